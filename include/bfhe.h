@@ -1,0 +1,140 @@
+/*
+ * bfhe.h -- C ABI of the B200-native gate-bootstrapping engine.
+ *
+ * This is the drop-in boundary beneath the reference's circuit evaluator.  Each entry point
+ * names the lbcrypto::BinFHEContext call (and the call site in /root/reference) it replaces.
+ * Plain pointers and sizes only; no C++ or torch types.  All functions return 0 on success and
+ * a negative code on error (text from bfhe_last_error()); nothing throws across this boundary.
+ *
+ * Ciphertexts: an LWE ciphertext mod q is ct_words = n+1 uint32 words (a_0..a_{n-1}, b) stored in a
+ * row of ct_stride words (ct_words rounded up to a multiple of 4).  A "slab" is a device array of
+ * such rows; gates name their operands by row index, exactly like the reference's registers
+ * (R<k> in the .out format, src/circuit.cpp:144-294).
+ *
+ * There is NO CPU fallback: every Eval* entry point runs hand-written sm_100a kernels and fails
+ * with BFHE_ERR_CUDA when no device is available.
+ */
+#ifndef BFHE_H
+#define BFHE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* enum values follow OpenFHE 1.0.x binfhe-constants.h (lbcrypto::BINFHE_PARAMSET / BINFHE_METHOD / BINGATE);
+ * the reference only ever passes TOY / STD128_OPT and AP / GINX (src/circuit.cpp:69-86, src/utils.cpp:165-190) */
+enum { BFHE_TOY = 0, BFHE_STD128_OPT = 5 };
+enum { BFHE_AP = 0, BFHE_GINX = 1 };
+enum { BFHE_OR = 0, BFHE_AND = 1, BFHE_NOR = 2, BFHE_NAND = 3, BFHE_XOR_FAST = 4, BFHE_XNOR_FAST = 5,
+       BFHE_XOR = 6, BFHE_XNOR = 7, /* composite OR(AND(a,!b),AND(!a,b)) as src/gate.cpp:198-202 */
+       BFHE_BOOTSTRAP = 8 /* BinFHEContext::Bootstrap: in1 ignored */ };
+#define BFHE_NEG0 0x100u /* operand 0 passes through EvalNOT first (fused, no bootstrap) */
+#define BFHE_NEG1 0x200u
+
+enum { BFHE_OK = 0, BFHE_ERR_ARG = -1, BFHE_ERR_STATE = -2, BFHE_ERR_CUDA = -3, BFHE_ERR_FORMAT = -4,
+       BFHE_ERR_ALIAS = -5 /* EvalBinGate(ct, ct): OpenFHE throws, src/gate.cpp:134 catches */,
+       BFHE_ERR_NCCL = -6, BFHE_ERR_IO = -7 };
+
+typedef struct {
+  uint32_t paramset, method;
+  uint32_t n, N, q;
+  uint64_t Q, qKS;
+  uint32_t baseKS, dKS, baseG, dG, baseR, dR;
+  uint32_t ct_words, ct_stride;
+} bfhe_params;
+
+/* one gate of a wavefront: replaces one Gate::Evaluate task (src/gate.cpp:49, src/circuit.cpp:698-710) */
+typedef struct {
+  uint32_t op; /* BFHE_<gate> | BFHE_NEG0 | BFHE_NEG1 */
+  uint32_t in0, in1, out; /* slab rows */
+} bfhe_gate;
+
+typedef struct bfhe_ctx bfhe_ctx;
+
+/* ---- context: BinFHEContext::GenerateBinFHEContext(set, method)  (src/circuit.cpp:88) ---- */
+bfhe_ctx *bfhe_create(int paramset, int method, int device /* CUDA ordinal, -1 = host-only (keygen/encrypt/decrypt) */);
+void bfhe_destroy(bfhe_ctx *);
+int bfhe_get_params(const bfhe_ctx *, bfhe_params *out);
+const char *bfhe_last_error(void);
+/* launch stream for every subsequent kernel (a cudaStream_t, e.g. torch's current stream); NULL = own stream */
+int bfhe_set_stream(bfhe_ctx *, void *cuda_stream);
+int bfhe_sync(bfhe_ctx *);
+
+/* ---- keys: KeyGen() / BTKeyGen(sk)  (src/circuit.cpp:90-91) ---- */
+int bfhe_keygen(bfhe_ctx *, uint64_t seed);   /* LWE secret key (host) */
+int bfhe_btkeygen(bfhe_ctx *, uint64_t seed); /* bootstrapping + key-switching keys (host), uploaded if a device is attached */
+/* flat key blob ("same serialized keys" contract, SURVEY 5 checkpoint/resume): layout documented in DESIGN.md:
+ *   header{magic "BFHEKEY1", version, params, has_sk, ksk_elem_bytes, Q, qKS, bk_words, ksk_elems}
+ *   sk[n] int32 | BK coefficient form uint32 | KSK [N][baseKS][dKS][n+1] uint16 (qKS<=2^16) or uint32 */
+size_t bfhe_keyblob_size(const bfhe_ctx *);
+int bfhe_export_keys(const bfhe_ctx *, void *buf, size_t cap, int include_sk);
+int bfhe_import_keys(bfhe_ctx *, const void *buf, size_t len);
+int bfhe_save_keys(const bfhe_ctx *, const char *path, int include_sk);
+int bfhe_load_keys(bfhe_ctx *, const char *path);
+
+/* ---- host-side LWE: Encrypt(sk, bit, FRESH) / Decrypt(sk, ct, &res)  (src/circuit.cpp:506,800; src/gate.cpp:72..) ---- */
+int bfhe_encrypt(const bfhe_ctx *, const uint8_t *bits, size_t count, uint64_t seed, uint32_t *ct_host /* count*ct_stride */);
+int bfhe_decrypt(const bfhe_ctx *, const uint32_t *ct_host, size_t count, uint8_t *out /* floor(4r/q) in 0..3 */);
+
+/* ---- device slabs (wire storage; replaces Wire::ct shared_ptrs, src/wire.h:46-73) ---- */
+int bfhe_slab_alloc(bfhe_ctx *, size_t rows, uint32_t **dev_ptr);
+int bfhe_slab_free(bfhe_ctx *, uint32_t *dev_ptr);
+int bfhe_slab_upload(bfhe_ctx *, uint32_t *dev_slab, size_t first_row, const uint32_t *host, size_t rows);
+int bfhe_slab_download(bfhe_ctx *, const uint32_t *dev_slab, size_t first_row, uint32_t *host, size_t rows);
+
+/* ---- the hot path ---- */
+/* EvalNOT(ct) for a batch (src/gate.cpp:112) */
+int bfhe_eval_not_batch(bfhe_ctx *, uint32_t *dev_slab, const uint32_t *in_rows, const uint32_t *out_rows, size_t count);
+/* EvalBinGate(gate, ct1, ct2) for one wavefront of independent gates (src/gate.cpp:133,146,172,200-202).
+ * gates is a HOST array; XOR/XNOR expand to the reference's 3-bootstrap composite.  Asynchronous on the stream. */
+int bfhe_eval_bingate_batch(bfhe_ctx *, uint32_t *dev_slab, const bfhe_gate *gates, size_t count);
+/* Bootstrap(ct) for a batch (what Encrypt's BOOTSTRAPPED default applies to every input, src/circuit.cpp:506) */
+int bfhe_bootstrap_batch(bfhe_ctx *, uint32_t *dev_slab, const uint32_t *in_rows, const uint32_t *out_rows, size_t count);
+/* end-to-end form with HOST buffers: H2D of the input slab rows, the wavefront, D2H of the produced rows.
+ * in_host holds rows [0, in_rows) of the slab; gate.out rows are >= in_rows and < in_rows + out_rows. */
+int bfhe_eval_bingate_host(bfhe_ctx *, const bfhe_gate *gates, size_t count, const uint32_t *in_host, size_t in_rows,
+                           uint32_t *out_host, size_t out_rows);
+
+/* ---- measurement hooks ---- */
+/* when enabled, every hot-path launch is bracketed by CUDA events on the launch stream */
+int bfhe_profile_enable(bfhe_ctx *, int on);
+/* kernel: 0 = blind rotation, 1 = key switch, 2 = EvalNOT; returns accumulated device ms and launch count, then resets */
+int bfhe_profile_read(bfhe_ctx *, int kernel, double *ms, uint64_t *launches);
+/* integer-pipe microbenchmark: measured 32-bit multiply-class instructions/s (IMAD, IMAD.HI, IMAD.WIDE) */
+int bfhe_microbench_int(bfhe_ctx *, int which, double *ginstr_per_s);
+
+/* ---- stage-level entry points (parity tests against the oracle; same kernels the hot path launches) ---- */
+int bfhe_dbg_ntt_roundtrip(bfhe_ctx *, const uint32_t *poly_host, size_t npoly, uint32_t *fwd_inv_host, uint32_t *prod_host,
+                           const uint32_t *poly2_host);
+/* blind rotation only: acc in coefficient form (2N words per gate) */
+int bfhe_dbg_blind_rotate(bfhe_ctx *, uint32_t *dev_slab, const bfhe_gate *gates, size_t count, uint32_t *acc_host);
+/* test hook: force the number of gates one CTA carries (1, 2 or 4; 0 = choose from the batch size) */
+int bfhe_dbg_set_gates_per_cta(bfhe_ctx *, int gates_per_cta);
+
+/* ---- circuit evaluator: mirrors class Circuit (src/circuit.h:56-72), level-synchronous ---- */
+typedef struct bfhe_circuit bfhe_circuit;
+bfhe_circuit *bfhe_circuit_create(bfhe_ctx *);
+void bfhe_circuit_destroy(bfhe_circuit *);
+int bfhe_circuit_read_file(bfhe_circuit *, const char *path);             /* Circuit::ReadFile (.out assembler format) */
+int bfhe_circuit_read_bristol(bfhe_circuit *, const char *path, int new_format); /* analyze+assemble without the text round trip */
+int bfhe_circuit_set_flags(bfhe_circuit *, int plaintext, int encrypted, int verify); /* setPlaintext/Encrypted/Verify */
+int bfhe_circuit_info(const bfhe_circuit *, uint32_t *n_inputs, uint32_t *input_bits /*[8]*/, uint32_t *n_output_bits,
+                      uint32_t *n_gates, uint32_t *n_bootstraps, uint32_t *n_levels, uint32_t *max_width);
+/* multi-GPU: shard every level over world ranks; comm_id = 128-byte ncclUniqueId distributed by the caller */
+int bfhe_circuit_set_sharding(bfhe_circuit *, int rank, int world, const void *nccl_unique_id);
+int bfhe_get_nccl_unique_id(void *out128);
+int bfhe_circuit_reset(bfhe_circuit *);                                     /* Circuit::Reset */
+int bfhe_circuit_set_input(bfhe_circuit *, const uint8_t *bits, size_t nbits, uint64_t seed); /* Circuit::SetInput (all input buses concatenated) */
+int bfhe_circuit_clock(bfhe_circuit *, uint8_t *out_bits, size_t cap, uint8_t *plain_out_bits); /* Circuit::Clock */
+int bfhe_circuit_stats(const bfhe_circuit *, double *device_ms, double *host_ms, uint64_t *verify_mismatches);
+/* per-level plan, for tests of the sharding logic: gates of level L assigned to `rank` of `world` */
+int bfhe_circuit_level_plan(const bfhe_circuit *, uint32_t level, int rank, int world, bfhe_gate *out, size_t cap,
+                            uint32_t *count, uint32_t *first_row, uint32_t *rows_per_rank);
+int bfhe_circuit_dump_gate_count(const bfhe_circuit *, uint32_t *in, uint32_t *out, uint32_t *and_, uint32_t *or_,
+                                 uint32_t *xor_, uint32_t *not_);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

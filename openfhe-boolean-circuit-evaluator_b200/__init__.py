@@ -1,0 +1,281 @@
+"""Python host-side mirror of the C ABI in include/bfhe.h (ctypes; plumbing only).
+
+The product is the sm_100a shared library ``libbfhe_b200.so`` built in-tree by ``build.py``;
+this module binds it 1:1.  It contains no arithmetic and no fallback: if the library is missing,
+import fails loudly; if no CUDA device is present, every Eval* call raises BfheError.
+
+Directory name contains '-', so import it through ``load_package()`` in ``bfhe_loader.py`` at the repo
+root (tests/conftest.py and bench.py do), which registers it as module ``bfhe_b200``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbfhe_b200.so")
+
+TOY, STD128_OPT = 0, 5
+AP, GINX = 0, 1
+OR, AND, NOR, NAND, XOR_FAST, XNOR_FAST, XOR, XNOR, BOOTSTRAP = range(9)
+NEG0, NEG1 = 0x100, 0x200
+ERR_ARG, ERR_STATE, ERR_CUDA, ERR_FORMAT, ERR_ALIAS, ERR_NCCL, ERR_IO = -1, -2, -3, -4, -5, -6, -7
+
+GATE_DTYPE = np.dtype([("op", "<u4"), ("in0", "<u4"), ("in1", "<u4"), ("out", "<u4")])
+
+
+class Params(C.Structure):
+    _fields_ = [("paramset", C.c_uint32), ("method", C.c_uint32), ("n", C.c_uint32), ("N", C.c_uint32),
+                ("q", C.c_uint32), ("Q", C.c_uint64), ("qKS", C.c_uint64), ("baseKS", C.c_uint32),
+                ("dKS", C.c_uint32), ("baseG", C.c_uint32), ("dG", C.c_uint32), ("baseR", C.c_uint32),
+                ("dR", C.c_uint32), ("ct_words", C.c_uint32), ("ct_stride", C.c_uint32)]
+
+
+class BfheError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("bfhe error %d: %s" % (code, msg))
+        self.code = code
+
+
+# every symbol include/bfhe.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "bfhe_create", "bfhe_destroy", "bfhe_get_params", "bfhe_last_error", "bfhe_set_stream", "bfhe_sync",
+    "bfhe_keygen", "bfhe_btkeygen", "bfhe_keyblob_size", "bfhe_export_keys", "bfhe_import_keys", "bfhe_save_keys",
+    "bfhe_load_keys", "bfhe_encrypt", "bfhe_decrypt", "bfhe_slab_alloc", "bfhe_slab_free", "bfhe_slab_upload",
+    "bfhe_slab_download", "bfhe_eval_not_batch", "bfhe_eval_bingate_batch", "bfhe_bootstrap_batch",
+    "bfhe_eval_bingate_host", "bfhe_profile_enable", "bfhe_profile_read", "bfhe_microbench_int",
+    "bfhe_dbg_ntt_roundtrip", "bfhe_dbg_blind_rotate", "bfhe_dbg_set_gates_per_cta",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libbfhe_b200.so is not built: run `python __graft_entry__.py` (build()) first; "
+                          "there is no fallback implementation")
+    L = C.CDLL(LIB_PATH)
+    vp, u32p, u8p, sz = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.c_size_t
+    L.bfhe_create.restype = vp
+    L.bfhe_create.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.bfhe_destroy.argtypes = [vp]
+    L.bfhe_destroy.restype = None
+    L.bfhe_get_params.argtypes = [vp, C.POINTER(Params)]
+    L.bfhe_last_error.restype = C.c_char_p
+    L.bfhe_set_stream.argtypes = [vp, vp]
+    L.bfhe_sync.argtypes = [vp]
+    L.bfhe_keygen.argtypes = [vp, C.c_uint64]
+    L.bfhe_btkeygen.argtypes = [vp, C.c_uint64]
+    L.bfhe_keyblob_size.restype = sz
+    L.bfhe_keyblob_size.argtypes = [vp]
+    L.bfhe_export_keys.argtypes = [vp, vp, sz, C.c_int]
+    L.bfhe_import_keys.argtypes = [vp, vp, sz]
+    L.bfhe_save_keys.argtypes = [vp, C.c_char_p, C.c_int]
+    L.bfhe_load_keys.argtypes = [vp, C.c_char_p]
+    L.bfhe_encrypt.argtypes = [vp, vp, sz, C.c_uint64, vp]
+    L.bfhe_decrypt.argtypes = [vp, vp, sz, vp]
+    L.bfhe_slab_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.bfhe_slab_free.argtypes = [vp, vp]
+    L.bfhe_slab_upload.argtypes = [vp, vp, sz, vp, sz]
+    L.bfhe_slab_download.argtypes = [vp, vp, sz, vp, sz]
+    L.bfhe_eval_not_batch.argtypes = [vp, vp, vp, vp, sz]
+    L.bfhe_eval_bingate_batch.argtypes = [vp, vp, vp, sz]
+    L.bfhe_bootstrap_batch.argtypes = [vp, vp, vp, vp, sz]
+    L.bfhe_eval_bingate_host.argtypes = [vp, vp, sz, vp, sz, vp, sz]
+    L.bfhe_profile_enable.argtypes = [vp, C.c_int]
+    L.bfhe_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.bfhe_microbench_int.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.bfhe_dbg_ntt_roundtrip.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.bfhe_dbg_blind_rotate.argtypes = [vp, vp, vp, sz, vp]
+    L.bfhe_dbg_set_gates_per_cta.argtypes = [vp, C.c_int]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Slab:
+    """A device array of ciphertext rows (wire storage)."""
+
+    def __init__(self, ctx, rows):
+        self.ctx, self.rows = ctx, rows
+        p = C.c_void_p()
+        ctx._ck(ctx.L.bfhe_slab_alloc(ctx.h, rows, C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, host, first_row=0):
+        host = np.ascontiguousarray(host, dtype=np.uint32)
+        assert host.ndim == 2 and host.shape[1] == self.ctx.stride
+        self.ctx._ck(self.ctx.L.bfhe_slab_upload(self.ctx.h, self.ptr, first_row, _ptr(host), host.shape[0]))
+        self.ctx.sync()
+
+    def download(self, first_row=0, rows=None):
+        rows = self.rows - first_row if rows is None else rows
+        out = np.empty((rows, self.ctx.stride), dtype=np.uint32)
+        self.ctx._ck(self.ctx.L.bfhe_slab_download(self.ctx.h, self.ptr, first_row, _ptr(out), rows))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.L.bfhe_slab_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """BinFHEContext-shaped handle: GenerateBinFHEContext / KeyGen / BTKeyGen / Encrypt / Decrypt /
+    EvalNOT / EvalBinGate / Bootstrap (src/circuit.cpp:88-91,506,800; src/gate.cpp:112,133 in the reference)."""
+
+    def __init__(self, paramset=STD128_OPT, method=GINX, device=0):
+        self.L = lib()
+        self.h = self.L.bfhe_create(paramset, method, device)
+        if not self.h:
+            raise BfheError(ERR_ARG, self.L.bfhe_last_error().decode())
+        self.p = Params()
+        self.L.bfhe_get_params(self.h, C.byref(self.p))
+        self.stride = self.p.ct_stride
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.bfhe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise BfheError(rc, self.L.bfhe_last_error().decode())
+
+    # keys
+    def keygen(self, seed=1):
+        self._ck(self.L.bfhe_keygen(self.h, seed))
+
+    def btkeygen(self, seed=2):
+        self._ck(self.L.bfhe_btkeygen(self.h, seed))
+
+    def export_keys(self, include_sk=True):
+        n = self.L.bfhe_keyblob_size(self.h)
+        buf = np.empty(n, dtype=np.uint8)
+        self._ck(self.L.bfhe_export_keys(self.h, _ptr(buf), n, int(include_sk)))
+        return buf
+
+    def import_keys(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._ck(self.L.bfhe_import_keys(self.h, _ptr(blob), blob.size))
+
+    def save_keys(self, path, include_sk=True):
+        self._ck(self.L.bfhe_save_keys(self.h, path.encode(), int(include_sk)))
+
+    def load_keys(self, path):
+        self._ck(self.L.bfhe_load_keys(self.h, path.encode()))
+
+    # host LWE
+    def encrypt(self, bits, seed=0):
+        bits = np.ascontiguousarray(np.asarray(bits).ravel(), dtype=np.uint8)
+        out = np.zeros((bits.size, self.stride), dtype=np.uint32)
+        self._ck(self.L.bfhe_encrypt(self.h, _ptr(bits), bits.size, seed, _ptr(out)))
+        return out
+
+    def decrypt(self, cts):
+        cts = np.ascontiguousarray(cts, dtype=np.uint32).reshape(-1, self.stride)
+        out = np.zeros(cts.shape[0], dtype=np.uint8)
+        self._ck(self.L.bfhe_decrypt(self.h, _ptr(cts), cts.shape[0], _ptr(out)))
+        return out
+
+    # device
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self.L.bfhe_set_stream(self.h, cuda_stream_handle))
+
+    def sync(self):
+        self._ck(self.L.bfhe_sync(self.h))
+
+    def slab(self, rows):
+        return Slab(self, rows)
+
+    @staticmethod
+    def _slab_ptr(slab):
+        return slab.ptr if isinstance(slab, Slab) else int(slab)
+
+    def eval_not_batch(self, slab, in_rows, out_rows):
+        i = np.ascontiguousarray(in_rows, dtype=np.uint32)
+        o = np.ascontiguousarray(out_rows, dtype=np.uint32)
+        self._ck(self.L.bfhe_eval_not_batch(self.h, self._slab_ptr(slab), _ptr(i), _ptr(o), i.size))
+
+    def eval_bingate_batch(self, slab, gates):
+        g = np.ascontiguousarray(gates, dtype=GATE_DTYPE)
+        self._ck(self.L.bfhe_eval_bingate_batch(self.h, self._slab_ptr(slab), _ptr(g), g.size))
+
+    def bootstrap_batch(self, slab, in_rows, out_rows):
+        i = np.ascontiguousarray(in_rows, dtype=np.uint32)
+        o = np.ascontiguousarray(out_rows, dtype=np.uint32)
+        self._ck(self.L.bfhe_bootstrap_batch(self.h, self._slab_ptr(slab), _ptr(i), _ptr(o), i.size))
+
+    def eval_bingate_host(self, gates, in_host, out_rows, out_host=None):
+        g = np.ascontiguousarray(gates, dtype=GATE_DTYPE)
+        assert in_host.dtype == np.uint32 and in_host.flags["C_CONTIGUOUS"]
+        if out_host is None:
+            out_host = np.empty((out_rows, self.stride), dtype=np.uint32)
+        self._ck(self.L.bfhe_eval_bingate_host(self.h, _ptr(g), g.size, _ptr(in_host), in_host.shape[0], _ptr(out_host),
+                                               out_rows))
+        return out_host
+
+    # single-gate conveniences with the reference's method names (batch of one)
+    def EvalBinGate(self, gate, ct1, ct2):
+        inp = np.stack([np.asarray(ct1, dtype=np.uint32), np.asarray(ct2, dtype=np.uint32)])
+        g = np.array([(gate, 0, 1, 2)], dtype=GATE_DTYPE)
+        return self.eval_bingate_host(g, np.ascontiguousarray(inp), 1)[0]
+
+    def EvalNOT(self, ct):
+        s = self.slab(2)
+        s.upload(np.asarray(ct, dtype=np.uint32).reshape(1, -1))
+        self.eval_not_batch(s, [0], [1])
+        out = s.download(1, 1)[0]
+        s.free()
+        return out
+
+    def Bootstrap(self, ct):
+        inp = np.ascontiguousarray(np.asarray(ct, dtype=np.uint32).reshape(1, -1))
+        g = np.array([(BOOTSTRAP, 0, 0, 1)], dtype=GATE_DTYPE)
+        return self.eval_bingate_host(g, inp, 1)[0]
+
+    # measurement
+    def profile_enable(self, on=True):
+        self._ck(self.L.bfhe_profile_enable(self.h, int(on)))
+
+    def profile_read(self, kernel):
+        ms, n = C.c_double(), C.c_uint64()
+        self._ck(self.L.bfhe_profile_read(self.h, kernel, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def microbench_int(self, which):
+        v = C.c_double()
+        self._ck(self.L.bfhe_microbench_int(self.h, which, C.byref(v)))
+        return v.value
+
+    # debug / parity
+    def dbg_ntt_roundtrip(self, a, b=None):
+        a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, self.p.N)
+        rt = np.empty_like(a)
+        prod = np.empty_like(a) if b is not None else None
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, self.p.N)
+        self._ck(self.L.bfhe_dbg_ntt_roundtrip(self.h, _ptr(a), a.shape[0], _ptr(rt), _ptr(prod), _ptr(b)))
+        return rt, prod
+
+    def dbg_blind_rotate(self, slab, gates):
+        g = np.ascontiguousarray(gates, dtype=GATE_DTYPE)
+        acc = np.empty((g.size, 2, self.p.N), dtype=np.uint32)
+        self._ck(self.L.bfhe_dbg_blind_rotate(self.h, self._slab_ptr(slab), _ptr(g), g.size, _ptr(acc)))
+        return acc
+
+    def dbg_set_gates_per_cta(self, g):
+        self._ck(self.L.bfhe_dbg_set_gates_per_cta(self.h, g))

@@ -1,0 +1,49 @@
+"""Build the sm_100a shared library in-tree (nvcc cross-compiles without a GPU)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+HOST = os.path.join(HERE, "host")
+LIB = os.path.join(HERE, "libbfhe_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+CCBIN = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def sources():
+    src = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cpp"))]
+    if os.path.isdir(HOST):
+        src += [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp")]
+    return src
+
+
+def deps():
+    d = sources()
+    for root in (CSRC, HOST, os.path.join(HERE, "..", "include")):
+        if os.path.isdir(root):
+            d += [os.path.join(root, f) for f in os.listdir(root) if f.endswith((".h", ".hpp", ".cuh"))]
+    return d
+
+
+def build(force=False, verbose=False):
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in deps()):
+        return LIB
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    common = [NVCC, "-ccbin", CCBIN, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
+              "-Xcompiler", "-fPIC,-fopenmp,-O3", "-I", os.path.join(HERE, "..", "include")]
+    if verbose:
+        common += ["-Xptxas", "-v"]
+    for s in sources():
+        o = os.path.join(HERE, "build", os.path.basename(s) + ".o")
+        if force or not os.path.exists(o) or any(os.path.getmtime(d) > os.path.getmtime(o) for d in deps()):
+            cmd = common + (["-x", "cu"] if s.endswith(".cpp") else []) + ["-c", s, "-o", o]
+            subprocess.check_call(cmd)
+        objs.append(o)
+    subprocess.check_call([NVCC, "-ccbin", CCBIN, "-shared", "-o", LIB] + objs + ["-lgomp", "-ldl", "-cudart", "static"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

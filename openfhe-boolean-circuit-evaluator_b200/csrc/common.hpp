@@ -1,0 +1,66 @@
+// common.hpp -- types shared between the host engine and the sm_100a kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace bfhe {
+
+using u8 = uint8_t;
+using u16 = uint16_t;
+using u32 = uint32_t;
+using u64 = uint64_t;
+using i32 = int32_t;
+using i64 = int64_t;
+
+// Passed to every kernel as a __grid_constant__ parameter: lands in the constant bank, so the
+// compile-time-indexed "uniform" twiddles below become immediate-like operands of IMAD.
+struct DevConst {
+  u32 Q, Q2;       // ring modulus (2^26 < Q < 2^27) and 2Q
+  u32 qinv_neg;    // -Q^-1 mod 2^32 (Montgomery)
+  u32 mu;          // floor(2^32 / Q) (lazy Barrett)
+  u32 oneM;        // 2^32 mod Q  (Montgomery form of 1)
+  u32 Q8;          // Q/8 + 1
+  u32 n, N, q, factor; // LWE dim, ring dim, LWE modulus, 2N/q
+  u32 qKS, baseKS, dKS;
+  u32 baseR, dR, dG, logBG;
+  u32 ct_stride;
+  u32 ninv, ninvs; // N^-1 mod Q and its Shoup companion (debug kernels only)
+  u32 nM, nMs;     // N^-1 * 2^32 mod Q (+Shoup): coefficient-form key -> device form
+  u32 gate_const[9];
+  // psi^bitrev(k), k in [1,32): the twiddles of every NTT stage whose butterflies span >= 32 indices.
+  u32 tw[32], tws[32], itw[32], itws[32];
+};
+
+// one gate as the kernels see it (built on the host from bfhe_gate)
+struct DevGate {
+  const u32 *in0;
+  const u32 *in1;
+  u32 *out;
+  u32 op;
+  u32 pad;
+};
+
+enum : u32 { OP_OR = 0, OP_AND = 1, OP_NOR = 2, OP_NAND = 3, OP_XOR_FAST = 4, OP_XNOR_FAST = 5, OP_XOR = 6, OP_XNOR = 7,
+             OP_BOOTSTRAP = 8, OP_NEG0 = 0x100, OP_NEG1 = 0x200 };
+
+struct LaunchInfo { // filled by the launch helpers for the profiler hooks
+  int gates_per_cta;
+  int ctas;
+  size_t smem_bytes;
+};
+
+// kernels.cu entry points (all asynchronous on `stream`; return cudaError_t as int)
+int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates, int count, const u32 *d_bk,
+                        const u32 *d_twl /*fwd w | fwd ws | inv w | inv ws, each N words*/, const u32 *d_psiM,
+                        u32 *d_ext /*count * (N+4)*/, u32 *d_acc_dbg /*nullable: count*2*N*/, int force_gates_per_cta,
+                        void *stream, LaunchInfo *info);
+int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates, int count, const void *d_ksk,
+                     int ksk_elem_bytes, void *stream);
+int launch_eval_not(const DevConst &P, const u32 *const *d_in, u32 *const *d_out, int count, void *stream);
+int launch_bk_convert(const DevConst &P, const u32 *d_coef, u32 *d_dev, size_t npoly, const u32 *d_twl, void *stream);
+int launch_dbg_ntt(const DevConst &P, const u32 *d_a, const u32 *d_b, u32 *d_rt, u32 *d_prod, int npoly, const u32 *d_twl,
+                   void *stream);
+int launch_microbench(int which, u32 *d_sink, int iters, int *threads_total, int *ops_per_thread_iter, void *stream);
+int blind_rotate_set_attrs();
+
+} // namespace bfhe

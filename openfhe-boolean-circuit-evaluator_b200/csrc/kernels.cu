@@ -1,0 +1,730 @@
+// kernels.cu -- hand-written sm_100a kernels for the gate-bootstrapping hot path.
+//
+// Replaces the arithmetic the reference reaches through lbcrypto::BinFHEContext::EvalBinGate /
+// Bootstrap / EvalNOT (src/gate.cpp:112,133,172,198-202 in /root/reference); stage list in
+// SURVEY.md 8(a) rows a8-a17.  Design notes (DESIGN.md has the full story):
+//
+//  * One warp owns one ring polynomial.  A size-N negacyclic NTT is two register passes of
+//    E = N/32 points per thread with ONE shared-memory transpose between them (plus one
+//    warp-shuffle butterfly stage when log2 N is odd).  No __syncthreads inside a transform.
+//  * Pass "wide" (butterfly span >= 32) uses twiddles that are uniform across the warp: they sit in
+//    the kernel-parameter constant bank and are consumed as constant operands by IMAD.
+//    Pass "narrow" (span < 32) uses 31 per-lane twiddles read as conflict-free LDS.128.
+//  * Arithmetic: 32-bit Shoup butterflies with lazy ranges (Q < 2^27, so the forward transform needs no
+//    correction at all: values grow by 2Q per stage and stay below 2^32); the RGSW x RLWE
+//    external product accumulates 2*dG 32x32->64 products per slot in one IMAD.WIDE chain and
+//    Montgomery-reduces once (keys are stored pre-multiplied by 2^32 * N^-1).
+//  * The accumulator lives in COEFFICIENT form in the registers of the warp that owns it for the
+//    whole blind rotation: each step is INTT(previous product) -> add -> signed digit decomposition
+//    -> dG forward NTTs, all in registers of the same warp.
+//  * A CTA carries G gates through the n blind-rotation steps in lock step so that every
+//    bootstrapping-key word loaded from L2 is reused G times from registers (GINX).
+#include "common.hpp"
+#include <cuda_runtime.h>
+
+namespace bfhe {
+
+// ------------------------------------------------------------------------------------------
+// modular arithmetic
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q) { return x * w - __umulhi(x, ws) * Q; } // [0,2Q)
+__device__ __forceinline__ u32 redc(u64 s, u32 Q, u32 qinv_neg) { // s * 2^-32 mod Q, lazy
+  u32 m = (u32)s * qinv_neg;
+  return (u32)((s + (u64)m * Q) >> 32);
+}
+__device__ __forceinline__ u32 lazy_reduce(u32 x, u32 Q, u32 mu) { return x - __umulhi(x, mu) * Q; } // any x -> [0,2Q)
+__device__ __forceinline__ u32 csub(u32 x, u32 Q) { return min(x, x - Q); }                            // [0,2Q) -> [0,Q)
+
+// ------------------------------------------------------------------------------------------
+// shared-memory polynomial layout: row t' (the E consecutive indices owned by lane t' in the narrow
+// pass) is E words; its 16-byte chunks are XOR-swizzled so that both the row access (LDS.128 by the
+// owning lane) and the column access (LDS.32 of index lane+32k by all lanes) are conflict free.
+// ------------------------------------------------------------------------------------------
+template <int E> struct Lay {
+  static constexpr int C = E / 4;
+  __device__ __forceinline__ static int swz(int tp) { return E == 32 ? (tp & 7) : ((tp >> 1) & 3); }
+  __device__ __forceinline__ static int chunk_off(int tp, int c) { return E * tp + 4 * (c ^ swz(tp)); }
+  __device__ __forceinline__ static int elem_off(int k, int lane) { // index lane + 32k
+    if (E == 32) return 32 * k + 4 * ((lane >> 2) ^ (k & 7)) + (lane & 3);
+    int j = lane & 15;
+    return 16 * (2 * k + (lane >> 4)) + 4 * ((j >> 2) ^ (k & 3)) + (j & 3);
+  }
+};
+template <int E> __device__ __forceinline__ void row_load(const u32 *buf, u32 (&x)[E], int lane) {
+#pragma unroll
+  for (int c = 0; c < E / 4; c++) {
+    uint4 v = *reinterpret_cast<const uint4 *>(buf + Lay<E>::chunk_off(lane, c));
+    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+  }
+}
+template <int E> __device__ __forceinline__ void row_store(u32 *buf, const u32 (&x)[E], int lane) {
+#pragma unroll
+  for (int c = 0; c < E / 4; c++)
+    *reinterpret_cast<uint4 *>(buf + Lay<E>::chunk_off(lane, c)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+}
+template <int E> __device__ __forceinline__ void col_load(const u32 *buf, u32 (&x)[E], int lane) {
+#pragma unroll
+  for (int k = 0; k < E; k++) x[k] = buf[Lay<E>::elem_off(k, lane)];
+}
+template <int E> __device__ __forceinline__ void col_store(u32 *buf, const u32 (&x)[E], int lane) {
+#pragma unroll
+  for (int k = 0; k < E; k++) buf[Lay<E>::elem_off(k, lane)] = x[k];
+}
+
+// per-lane twiddles of the narrow pass: smem table [C][32] of uint4, entry p of lane t' = psi^br(m+i)
+template <int E> __device__ __forceinline__ void load_lane_tw(const u32 *tab, u32 (&w)[E], int lane) {
+#pragma unroll
+  for (int c = 0; c < E / 4; c++) {
+    uint4 v = reinterpret_cast<const uint4 *>(tab)[c * 32 + lane];
+    w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// in-register passes.  The E-point sub-transform has the same shape in both passes: stage with
+// half-size t has E/(2t) groups, group gi uses twiddle number p = E/(2t) + gi of the pass's table.
+// ------------------------------------------------------------------------------------------
+// Cooley-Tukey (forward).  No range correction: x + T and x - T + 2Q grow by 2Q per stage.
+template <int E, bool UNI>
+__device__ __forceinline__ void ct_pass(u32 (&x)[E], const u32 *__restrict__ utw, const u32 *__restrict__ utws,
+                                        const u32 (&w)[E], const u32 (&ws)[E], u32 Q, u32 Q2) {
+#pragma unroll
+  for (int t = E / 2; t >= 1; t >>= 1) {
+#pragma unroll
+    for (int gi = 0; gi < E / (2 * t); gi++) {
+      const int p = E / (2 * t) + gi;
+      const u32 ww = UNI ? utw[p] : w[p], wws = UNI ? utws[p] : ws[p];
+#pragma unroll
+      for (int j = 0; j < t; j++) {
+        const int a = gi * 2 * t + j, b = a + t;
+        u32 T = mul_shoup(x[b], ww, wws, Q);
+        x[b] = x[a] - T + Q2;
+        x[a] = x[a] + T;
+      }
+    }
+  }
+}
+
+// Gentleman-Sande (inverse, unscaled).  B = bound of the inputs in units of Q (<= 16).  Sums double
+// per stage; when they would pass 32Q (= just under 2^32) they are pulled back below 2Q with one
+// lazy Barrett step.  Differences go through the Shoup multiply, which accepts any 32-bit input.
+template <int E, int T, int B, bool UNI, int MAXLAST> struct GsRun {
+  static constexpr int NB = 2 * B;
+  static constexpr bool LAST = (2 * T >= E);
+  static constexpr bool RED = LAST ? (NB > MAXLAST) : (NB > 16); // pull the sums back below 2Q after this stage?
+  static constexpr int OUTB = RED ? 2 : NB;
+  __device__ __forceinline__ static void run(u32 (&x)[E], const u32 *__restrict__ utw, const u32 *__restrict__ utws,
+                                             const u32 (&w)[E], const u32 (&ws)[E], u32 Q, u32 mu) {
+    static_assert(B <= 16, "GS input bound too large");
+    const u32 off = B * Q;
+#pragma unroll
+    for (int gi = 0; gi < E / (2 * T); gi++) {
+      const int p = E / (2 * T) + gi;
+      const u32 ww = UNI ? utw[p] : w[p], wws = UNI ? utws[p] : ws[p];
+#pragma unroll
+      for (int j = 0; j < T; j++) {
+        const int a = gi * 2 * T + j, b = a + T;
+        u32 S = x[a] + x[b];
+        u32 D = x[a] - x[b] + off;
+        x[b] = mul_shoup(D, ww, wws, Q);
+        x[a] = RED ? lazy_reduce(S, Q, mu) : S;
+      }
+    }
+    if constexpr (!LAST) GsRun<E, 2 * T, OUTB, UNI, MAXLAST>::run(x, utw, utws, w, ws, Q, mu);
+  }
+};
+// bound (in units of Q) of the values GsRun<E,1,B0,*,MAXLAST> leaves behind
+__host__ __device__ constexpr int gs_out_bound(int E, int B0, int MAXLAST) {
+  int B = B0;
+  for (int T = 1; T < E; T *= 2) {
+    const int NB = 2 * B;
+    const bool last = 2 * T >= E;
+    B = (last ? NB > MAXLAST : NB > 16) ? 2 : NB;
+  }
+  return B;
+}
+
+// ------------------------------------------------------------------------------------------
+// whole transforms (one warp, E values per lane)
+// ------------------------------------------------------------------------------------------
+struct TwTabs { // shared-memory per-lane twiddle tables, each N words
+  const u32 *fw, *fws, *iw, *iws;
+};
+
+// forward: x in column layout (index lane+32k, coefficient form, values < Q) -> row layout (index E*lane+j,
+// evaluation form, lazy < (2*logN+1)Q).  buf: N-word smem scratch, left holding garbage.
+template <int LOGN> __device__ __forceinline__ void ntt_forward(u32 (&x)[(1 << LOGN) / 32], u32 *buf, const DevConst &P,
+                                                               const TwTabs &tt, int lane) {
+  constexpr int E = (1 << LOGN) / 32;
+  const u32 Q = P.Q, Q2 = P.Q2;
+  u32 w[E], ws[E];
+  ct_pass<E, true>(x, P.tw, P.tws, w, ws, Q, Q2);
+  if constexpr (LOGN & 1) { // span-16 stage across lanes (lane bit 4): group index = k, twiddle psi_br[16+k]
+    const bool up = lane & 16;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      u32 v = up ? mul_shoup(x[k], P.tw[16 + k], P.tws[16 + k], Q) : x[k];
+      u32 o = __shfl_xor_sync(0xffffffffu, v, 16);
+      x[k] = up ? (o - v + Q2) : (v + o);
+    }
+  }
+  __syncwarp();
+  col_store<E>(buf, x, lane);
+  __syncwarp();
+  row_load<E>(buf, x, lane);
+  load_lane_tw<E>(tt.fw, w, lane);
+  load_lane_tw<E>(tt.fws, ws, lane);
+  ct_pass<E, false>(x, P.tw, P.tws, w, ws, Q, Q2);
+}
+
+// inverse (unscaled: N * true value; the keys carry N^-1): x in row layout (evaluation form, values < B0*Q)
+// -> column layout, coefficient form, fully reduced to [0,Q).
+template <int LOGN, int B0> __device__ __forceinline__ void ntt_inverse(u32 (&x)[(1 << LOGN) / 32], u32 *buf, const DevConst &P,
+                                                                        const TwTabs &tt, int lane) {
+  constexpr int E = (1 << LOGN) / 32;
+  const u32 Q = P.Q, mu = P.mu;
+  u32 w[E], ws[E];
+  load_lane_tw<E>(tt.iw, w, lane);
+  load_lane_tw<E>(tt.iws, ws, lane);
+  constexpr int ML = (LOGN & 1) ? 8 : 16; // what the next stage can take
+  GsRun<E, 1, B0, false, ML>::run(x, P.itw, P.itws, w, ws, Q, mu);
+  constexpr int B1 = gs_out_bound(E, B0, ML);
+  __syncwarp();
+  row_store<E>(buf, x, lane);
+  __syncwarp();
+  col_load<E>(buf, x, lane);
+  if constexpr (LOGN & 1) {
+    static_assert(B1 <= 8, "bound");
+    const bool up = lane & 16;
+    const u32 off = B1 * Q;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      u32 o = __shfl_xor_sync(0xffffffffu, x[k], 16);
+      // lower lane: U + V ; upper lane: (U - V) * w
+      u32 D = o - x[k] + off;
+      x[k] = up ? mul_shoup(D, P.itw[16 + k], P.itws[16 + k], Q) : (x[k] + o);
+    }
+    constexpr int B2 = 2 * B1;
+    GsRun<E, 1, B2, true, 32>::run(x, P.itw, P.itws, w, ws, Q, mu);
+  } else {
+    GsRun<E, 1, B1, true, 32>::run(x, P.itw, P.itws, w, ws, Q, mu);
+  }
+#pragma unroll
+  for (int k = 0; k < E; k++) x[k] = csub(lazy_reduce(x[k], Q, mu), Q);
+}
+
+// ------------------------------------------------------------------------------------------
+// blind rotation
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 brev(u32 x, int bits) { return __brev(x) >> (32 - bits); }
+
+template <int LOGN, int DG, int LOGBG, int G, bool AP> struct BrCfg {
+  static constexpr int N = 1 << LOGN, E = N / 32, C = E / 4, ROWS = 2 * DG;
+  static constexpr int W = 2 * G, THREADS = 32 * W;
+  static constexpr int NPAD = 1024; // per-gate index table (>= n*dR)
+  static constexpr size_t dct_words = (size_t)G * ROWS * N;
+  static constexpr size_t smem_bytes = (dct_words + 4 * N + (AP ? 0 : 2 * N)) * 4 + (size_t)G * NPAD * 2;
+};
+
+template <int LOGN, int DG, int LOGBG, int G, bool AP>
+__global__ void __launch_bounds__(64 * G, 1)
+blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count,
+                    const u32 *__restrict__ bk, const u32 *__restrict__ g_twl, const u32 *__restrict__ g_psiM,
+                    u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
+  using Cfg = BrCfg<LOGN, DG, LOGBG, G, AP>;
+  constexpr int N = Cfg::N, E = Cfg::E, C = Cfg::C, ROWS = Cfg::ROWS, W = Cfg::W, NPAD = Cfg::NPAD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u32 *dct = reinterpret_cast<u32 *>(smem_raw);                 // [G][ROWS][N]
+  u32 *s_tw = dct + Cfg::dct_words;                             // fw | fws | iw | iws
+  u32 *s_psiM = s_tw + 4 * N;                                   // [2N] Montgomery psi^k (GINX)
+  u16 *s_idx = reinterpret_cast<u16 *>(s_psiM + (AP ? 0 : 2 * N)); // [G][NPAD]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = warp >> 1, c = warp & 1; // this warp owns accumulator component c of gate g
+  const int gate0 = blockIdx.x * G;
+  const int gcount = min(G, count - gate0);
+  const u32 Q = P.Q, q = P.q, n = P.n;
+
+  for (int i = tid; i < 4 * N; i += Cfg::THREADS) s_tw[i] = g_twl[i];
+  if (!AP)
+    for (int i = tid; i < 2 * N; i += Cfg::THREADS) s_psiM[i] = g_psiM[i];
+  const TwTabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
+
+  // ---- prologue: LWE prep (EvalBinGate's ct1+ct2 / 2(ct1-ct2) / Bootstrap's b+q/4, with fused EvalNOT) ----
+  __shared__ u32 s_b[G];
+  for (int gg = 0; gg < gcount; gg++) {
+    const DevGate dg = gates[gate0 + gg];
+    const u32 gate = dg.op & 0xff;
+    for (u32 i = tid; i <= n; i += Cfg::THREADS) {
+      u32 x = dg.in0[i];
+      if (dg.op & OP_NEG0) x = (i == n) ? (q / 4 + q - x) % q : (q - x) % q;
+      u32 v;
+      if (gate == OP_BOOTSTRAP) {
+        v = (i == n) ? (x + q / 4) % q : x;
+      } else {
+        u32 y = dg.in1[i];
+        if (dg.op & OP_NEG1) y = (i == n) ? (q / 4 + q - y) % q : (q - y) % q;
+        v = (gate == OP_XOR_FAST || gate == OP_XNOR_FAST) ? (2 * (x + q - y)) % q : (x + y) % q;
+      }
+      if (i == n) s_b[gg] = v;
+      else {
+        u32 aneg = (q - v) % q;
+        if (!AP) s_idx[gg * NPAD + i] = (u16)(aneg * P.factor); // monomial exponent in [0,2N)
+        else {
+          u32 a = aneg;
+          for (u32 k = 0; k < P.dR; k++, a /= P.baseR) s_idx[gg * NPAD + i * P.dR + k] = (u16)(a % P.baseR);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- accumulator init: acc = (0, testvector) in coefficient form, column layout ----
+  const bool gvalid = g < gcount;
+  u32 acc[E];
+#pragma unroll
+  for (int k = 0; k < E; k++) acc[k] = 0;
+  if (gvalid && c == 1) {
+    const u32 gate = gates[gate0 + g].op & 0xff;
+    const u32 q1 = P.gate_const[gate == OP_BOOTSTRAP ? OP_AND : gate], q2 = (q1 + q / 2) % q;
+    const u32 b = s_b[g], Q8 = P.Q8, Q8n = Q - P.Q8;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const u32 idx = lane + 32 * k;
+      if (idx % P.factor == 0) {
+        const u32 t = (b + q - idx / P.factor) % q;
+        const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
+        acc[k] = in ? Q8n : Q8;
+      }
+    }
+  }
+
+  const int nsteps = AP ? n * P.dR : n;
+  bool pending = false;
+  u32 *mybuf = dct + ((size_t)g * ROWS + c) * N; // R[g][c] aliases dct row c of gate g
+
+  // MAC work split: item -> (chunk qc, gate split)
+  constexpr int GS = (W >= C) ? (W / C) : 1;
+  const u32 eA = 2 * brev(lane, 5) + 1; // lane part of the evaluation-point exponent 2*br(idx)+1
+
+  for (int step = 0; step < nsteps; step++) {
+    // ================= phase A: one warp per (gate, component) =================
+    bool active = gvalid;
+    if (AP && gvalid) active = s_idx[g * NPAD + step] != 0;
+    if (active) {
+      if (pending) {
+        u32 x[E];
+        row_load<E>(mybuf, x, lane);
+        ntt_inverse<LOGN, AP ? 8 : 4>(x, mybuf, P, tt, lane);
+#pragma unroll
+        for (int k = 0; k < E; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
+      }
+      // SignedDigitDecompose (a12): centre, peel DG signed base-2^LOGBG digits, digit l of component c -> row c+2l
+      i32 d[E];
+#pragma unroll
+      for (int k = 0; k < E; k++) d[k] = (acc[k] < (Q >> 1)) ? (i32)acc[k] : (i32)acc[k] - (i32)Q;
+#pragma unroll
+      for (int l = 0; l < DG; l++) {
+        u32 x[E];
+#pragma unroll
+        for (int k = 0; k < E; k++) {
+          i32 r = (i32)((u32)d[k] << (32 - LOGBG)) >> (32 - LOGBG);
+          d[k] = (d[k] - r) >> LOGBG;
+          x[k] = min((u32)r, (u32)r + Q);
+        }
+        u32 *buf = dct + ((size_t)g * ROWS + c + 2 * l) * N;
+        ntt_forward<LOGN>(x, buf, P, tt, lane);
+        row_store<E>(buf, x, lane);
+      }
+    }
+    pending = pending || active;
+    __syncthreads();
+
+    // ================= phase B: external product, slot-parallel over the CTA =================
+    for (int item = warp; item < C * GS; item += W) {
+      const int qc = item % C, gs0 = item / C;
+      uint4 kr[AP ? 1 : 2][ROWS][2];
+      if (!AP) {
+        const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + (qc * 32 + lane) * 4;
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+#pragma unroll
+          for (int r = 0; r < ROWS; r++)
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++)
+              kr[s][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((s * ROWS + r) * 2 + cc) * N));
+      }
+      // exponent parts that depend on (chunk, slot-in-chunk)
+      u32 eB[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) eB[r] = 2 * ((brev(r, 2) << (LOGN - 2)) | (brev(qc, LOGN - 7) << 5));
+
+      for (int gg = gs0; gg < gcount; gg += GS) {
+        u32 fp[4], fn[4];
+        if (AP) {
+          const u32 a0 = s_idx[gg * NPAD + step];
+          if (a0 == 0) continue;
+          const u32 i = step / P.dR, k = step % P.dR;
+          const u32 *kb = bk + (((size_t)i * (P.baseR - 1) + (a0 - 1)) * P.dR + k) * (ROWS * 2) * N + (qc * 32 + lane) * 4;
+#pragma unroll
+          for (int r = 0; r < ROWS; r++)
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) kr[0][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)(r * 2 + cc) * N));
+        } else {
+          // monomial factors (X^m - 1), (X^-m - 1) at this thread's 4 evaluation points, Montgomery form
+          const u32 m = s_idx[gg * NPAD + step], mask = 2 * N - 1;
+          const u32 ia = (m * eA) & mask;
+          const u32 A = s_psiM[ia], Ai = s_psiM[(2 * N - ia) & mask];
+          const u32 om = Q - P.oneM;
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            const u32 ib = (m * eB[r]) & mask;
+            const u32 Bv = s_psiM[ib], Bi = s_psiM[(2 * N - ib) & mask];
+            fp[r] = redc((u64)A * Bv, Q, P.qinv_neg) + om;
+            fn[r] = redc((u64)Ai * Bi, Q, P.qinv_neg) + om;
+          }
+        }
+        u32 *gd = dct + (size_t)gg * ROWS * N + Lay<E>::chunk_off(lane, qc);
+        uint4 dv[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) dv[r] = *reinterpret_cast<const uint4 *>(gd + (size_t)r * N);
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          u32 out[4];
+#pragma unroll
+          for (int sl = 0; sl < 4; sl++) {
+            u64 sp = 0, sn = 0;
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+              const u32 dval = sl == 0 ? dv[r].x : sl == 1 ? dv[r].y : sl == 2 ? dv[r].z : dv[r].w;
+              const uint4 kp = kr[0][r][cc];
+              sp += (u64)dval * (sl == 0 ? kp.x : sl == 1 ? kp.y : sl == 2 ? kp.z : kp.w);
+              if (!AP) {
+                const uint4 kn = kr[AP ? 0 : 1][r][cc];
+                sn += (u64)dval * (sl == 0 ? kn.x : sl == 1 ? kn.y : sl == 2 ? kn.z : kn.w);
+              }
+            }
+            const u32 pp = redc(sp, Q, P.qinv_neg);
+            if (AP) out[sl] = pp;
+            else {
+              const u32 pn = redc(sn, Q, P.qinv_neg);
+              out[sl] = redc((u64)pp * fp[sl] + (u64)pn * fn[sl], Q, P.qinv_neg);
+            }
+          }
+          // R[gg][cc] overwrites dct row cc: this thread has already consumed that chunk of every row
+          *reinterpret_cast<uint4 *>(gd + (size_t)cc * N) = make_uint4(out[0], out[1], out[2], out[3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: last inverse transform, sample extraction (a14) and ModSwitch Q -> qKS (a15) ----
+  if (gvalid) {
+    if (pending) {
+      u32 x[E];
+      row_load<E>(mybuf, x, lane);
+      ntt_inverse<LOGN, AP ? 8 : 4>(x, mybuf, P, tt, lane);
+#pragma unroll
+      for (int k = 0; k < E; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
+    }
+    const size_t gi = (size_t)gate0 + g;
+    if (acc_dbg) {
+#pragma unroll
+      for (int k = 0; k < E; k++) acc_dbg[(gi * 2 + c) * N + lane + 32 * k] = acc[k];
+    }
+    u32 *e = ext + gi * (N + 4);
+    const u64 qKS = P.qKS;
+    if (c == 0) {
+#pragma unroll
+      for (int k = 0; k < E; k++) {
+        const u32 j = lane + 32 * k;
+        const u32 v = (j == 0) ? acc[k] : (acc[k] == 0 ? 0 : Q - acc[k]); // Transpose: a'_0 = a_0, a'_k = -a_{N-k}
+        const u32 pos = (j == 0) ? 0 : N - j;
+        e[pos] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+      }
+    } else if (lane == 0) {
+      const u32 v = csub(acc[0] + P.Q8, Q);
+      e[N] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+    }
+  }
+}
+
+template <int LOGN, int DG, int LOGBG, int G, bool AP>
+static int launch_br_inst(const DevConst &P, const DevGate *d_gates, int count, const u32 *d_bk, const u32 *d_twl,
+                          const u32 *d_psiM, u32 *d_ext, u32 *d_acc, cudaStream_t st, LaunchInfo *info) {
+  using Cfg = BrCfg<LOGN, DG, LOGBG, G, AP>;
+  auto kern = blind_rotate_kernel<LOGN, DG, LOGBG, G, AP>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  const int ctas = (count + G - 1) / G;
+  if (info) { info->gates_per_cta = G; info->ctas = ctas; info->smem_bytes = Cfg::smem_bytes; }
+  kern<<<ctas, Cfg::THREADS, Cfg::smem_bytes, st>>>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc);
+  return (int)cudaGetLastError();
+}
+
+template <int LOGN, int DG, int LOGBG, bool AP>
+static int launch_br_g(int G, const DevConst &P, const DevGate *d_gates, int count, const u32 *d_bk, const u32 *d_twl,
+                       const u32 *d_psiM, u32 *d_ext, u32 *d_acc, cudaStream_t st, LaunchInfo *info) {
+  switch (G) {
+  case 1: return launch_br_inst<LOGN, DG, LOGBG, 1, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
+  case 2: return launch_br_inst<LOGN, DG, LOGBG, 2, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
+  default: return launch_br_inst<LOGN, DG, LOGBG, 4, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
+  }
+}
+
+int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates, int count, const u32 *d_bk, const u32 *d_twl,
+                        const u32 *d_psiM, u32 *d_ext, u32 *d_acc_dbg, int force_g, void *stream, LaunchInfo *info) {
+  if (count <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // gates per CTA: fill the SMs first (latency), then share key traffic (throughput)
+  int G = force_g > 0 ? force_g : (count <= sms ? 1 : (count <= 2 * sms ? 2 : 4));
+  if (P.N == 1024 && P.dG == 4 && P.logBG == 7) {
+    return method_ap ? launch_br_g<10, 4, 7, true>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
+                     : launch_br_g<10, 4, 7, false>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);
+  }
+  if (P.N == 512 && P.dG == 3 && P.logBG == 9) {
+    return method_ap ? launch_br_g<9, 3, 9, true>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
+                     : launch_br_g<9, 3, 9, false>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);
+  }
+  return (int)cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------
+// key switch (a16) + ModSwitch qKS -> q (a17).  One CTA per gate; RG row groups x COLS column threads.
+// Device KSK layout: [i][j][digit][ROWLEN] so that the 2048 (N*dKS) rows a gate gathers are each one
+// contiguous, 128-byte-aligned run.  PACK16: two uint16 residues per 32-bit lane load (qKS <= 2^16,
+// a power of two, so accumulating mod 2^32 per half and masking at the end is exact).
+// ------------------------------------------------------------------------------------------
+template <bool PACK16, int COLS, int RG>
+__global__ void __launch_bounds__(COLS *RG) keyswitch_kernel(const __grid_constant__ DevConst P, const u32 *__restrict__ ext,
+                                                             const DevGate *__restrict__ gates, const void *__restrict__ ksk,
+                                                             int rowlen_words) {
+  extern __shared__ u32 s_row[]; // N*dKS row ids, then RG*COLS*2 partial sums (u64 for !PACK16)
+  const int N = P.N, dKS = P.dKS, nrows = N * dKS;
+  const int tid = threadIdx.x, col = tid % COLS, rg = tid / COLS;
+  const u32 *e = ext + (size_t)blockIdx.x * (N + 4);
+  for (int r = tid; r < nrows; r += COLS * RG) {
+    const int i = r / dKS, j = r % dKS;
+    u32 a = e[i];
+    for (int t = 0; t < j; t++) a /= P.baseKS;
+    s_row[r] = (u32)((i * dKS + j) * P.baseKS + a % P.baseKS);
+  }
+  __syncthreads();
+  u64 *s_part = reinterpret_cast<u64 *>(s_row + ((nrows + 1) & ~1));
+  const u32 *k32 = reinterpret_cast<const u32 *>(ksk);
+  const bool colok = col < rowlen_words;
+  if (PACK16) {
+    u32 lo = 0, hi = 0;
+    if (colok) {
+#pragma unroll 8
+      for (int r = rg; r < nrows; r += RG) {
+        const u32 w = __ldg(k32 + (size_t)s_row[r] * rowlen_words + col);
+        lo += w & 0xffffu;
+        hi += w >> 16;
+      }
+    }
+    s_part[(rg * COLS + col) * 2] = lo;
+    s_part[(rg * COLS + col) * 2 + 1] = hi;
+  } else {
+    u64 s = 0;
+    if (colok) {
+#pragma unroll 8
+      for (int r = rg; r < nrows; r += RG) s += __ldg(k32 + (size_t)s_row[r] * rowlen_words + col);
+    }
+    s_part[(rg * COLS + col) * 2] = s;
+  }
+  __syncthreads();
+  if (rg == 0 && colok) {
+    const u64 qKS = P.qKS, q = P.q;
+    u32 *out = gates[blockIdx.x].out;
+    const int n = P.n;
+    for (int h = 0; h < (PACK16 ? 2 : 1); h++) {
+      const int k = PACK16 ? 2 * col + h : col;
+      if (k > n) break;
+      u64 s = 0;
+      for (int r = 0; r < RG; r++) s += s_part[(r * COLS + col) * 2 + h];
+      s %= qKS;
+      const u64 base = (k == n) ? e[N] : 0; // out = (0, b) - sum of selected KSK rows
+      const u64 v = (base + qKS - s) % qKS;
+      out[k] = (u32)(((2 * v * q + qKS) / (2 * qKS)) % q); // RoundqQ, exact integer form
+    }
+  }
+}
+
+int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates, int count, const void *d_ksk, int elem_bytes,
+                     void *stream) {
+  if (count <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nrows = P.N * P.dKS;
+  if (elem_bytes == 2) {
+    constexpr int COLS = 256, RG = 4;
+    const int rowlen_words = 256; // 512 uint16 per row
+    size_t smem = (size_t)((nrows + 1) & ~1) * 4 + (size_t)RG * COLS * 2 * 8;
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(keyswitch_kernel<true, COLS, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+    keyswitch_kernel<true, COLS, RG><<<count, COLS * RG, smem, st>>>(P, d_ext, d_gates, d_ksk, rowlen_words);
+  } else {
+    constexpr int COLS = 128, RG = 4;
+    const int rowlen_words = P.ct_stride;
+    if (rowlen_words > COLS) return (int)cudaErrorInvalidValue;
+    size_t smem = (size_t)((nrows + 1) & ~1) * 4 + (size_t)RG * COLS * 2 * 8;
+    keyswitch_kernel<false, COLS, RG><<<count, COLS * RG, smem, st>>>(P, d_ext, d_gates, d_ksk, rowlen_words);
+  }
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// EvalNOT (a6): (-a, q/4 - b)
+// ------------------------------------------------------------------------------------------
+__global__ void eval_not_kernel(const __grid_constant__ DevConst P, const u32 *const *__restrict__ in, u32 *const *__restrict__ out) {
+  const u32 *x = in[blockIdx.x];
+  u32 *y = out[blockIdx.x];
+  const u32 q = P.q, n = P.n;
+  for (u32 i = threadIdx.x; i <= n; i += blockDim.x) y[i] = (i == n) ? (q / 4 + q - x[i]) % q : (q - x[i]) % q;
+}
+int launch_eval_not(const DevConst &P, const u32 *const *d_in, u32 *const *d_out, int count, void *stream) {
+  if (count <= 0) return 0;
+  eval_not_kernel<<<count, 128, 0, (cudaStream_t)stream>>>(P, d_in, d_out);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// bootstrapping-key conversion: canonical coefficient form -> device form
+// (forward NTT in this kernel's slot order, times N^-1 * 2^32, laid out [chunk][lane][4] per polynomial)
+// ------------------------------------------------------------------------------------------
+template <int LOGN> __global__ void __launch_bounds__(128) bk_convert_kernel(const __grid_constant__ DevConst P, const u32 *__restrict__ coef,
+                                                                             u32 *__restrict__ dev, size_t npoly,
+                                                                             const u32 *__restrict__ g_twl) {
+  constexpr int N = 1 << LOGN, E = N / 32;
+  __shared__ __align__(16) u32 s_tw[4 * N];
+  __shared__ __align__(16) u32 s_buf[4][N];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 4 * N; i += blockDim.x) s_tw[i] = g_twl[i];
+  __syncthreads();
+  const TwTabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
+  for (size_t p = (size_t)blockIdx.x * 4 + warp; p < npoly; p += (size_t)gridDim.x * 4) {
+    u32 x[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) x[k] = coef[p * N + lane + 32 * k];
+    ntt_forward<LOGN>(x, s_buf[warp], P, tt, lane);
+#pragma unroll
+    for (int c = 0; c < E / 4; c++) {
+      u32 o[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) o[r] = csub(mul_shoup(x[4 * c + r], P.nM, P.nMs, P.Q), P.Q);
+      *reinterpret_cast<uint4 *>(dev + p * N + (c * 32 + lane) * 4) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __syncwarp();
+  }
+}
+int launch_bk_convert(const DevConst &P, const u32 *d_coef, u32 *d_dev, size_t npoly, const u32 *d_twl, void *stream) {
+  if (npoly == 0) return 0;
+  int blocks = (int)((npoly + 3) / 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (P.N == 1024) bk_convert_kernel<10><<<blocks, 128, 0, (cudaStream_t)stream>>>(P, d_coef, d_dev, npoly, d_twl);
+  else if (P.N == 512) bk_convert_kernel<9><<<blocks, 128, 0, (cudaStream_t)stream>>>(P, d_coef, d_dev, npoly, d_twl);
+  else return (int)cudaErrorInvalidValue;
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// debug / parity kernel: rt = INTT(NTT(a)), prod = a (*) b negacyclic, through the same transforms
+// ------------------------------------------------------------------------------------------
+template <int LOGN> __global__ void __launch_bounds__(32) dbg_ntt_kernel(const __grid_constant__ DevConst P, const u32 *__restrict__ a,
+                                                                         const u32 *__restrict__ b, u32 *__restrict__ rt,
+                                                                         u32 *__restrict__ prod, const u32 *__restrict__ g_twl) {
+  constexpr int N = 1 << LOGN, E = N / 32;
+  __shared__ __align__(16) u32 s_tw[4 * N];
+  __shared__ __align__(16) u32 s_buf[N];
+  const int lane = threadIdx.x;
+  for (int i = lane; i < 4 * N; i += 32) s_tw[i] = g_twl[i];
+  __syncwarp();
+  const TwTabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
+  const size_t p = blockIdx.x;
+  const u32 Q = P.Q;
+  u32 x[E], y[E];
+#pragma unroll
+  for (int k = 0; k < E; k++) x[k] = a[p * N + lane + 32 * k];
+  ntt_forward<LOGN>(x, s_buf, P, tt, lane);
+#pragma unroll
+  for (int k = 0; k < E; k++) y[k] = csub(lazy_reduce(x[k], Q, P.mu), Q);
+  {
+    u32 z[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) z[k] = y[k];
+    __syncwarp();
+    ntt_inverse<LOGN, 2>(z, s_buf, P, tt, lane);
+#pragma unroll
+    for (int k = 0; k < E; k++) rt[p * N + lane + 32 * k] = csub(mul_shoup(z[k], P.ninv, P.ninvs, Q), Q);
+  }
+  if (b) {
+    u32 z[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) z[k] = b[p * N + lane + 32 * k];
+    __syncwarp();
+    ntt_forward<LOGN>(z, s_buf, P, tt, lane);
+#pragma unroll
+    for (int k = 0; k < E; k++) z[k] = (u32)(((u64)csub(lazy_reduce(z[k], Q, P.mu), Q) * y[k]) % Q);
+    __syncwarp();
+    ntt_inverse<LOGN, 2>(z, s_buf, P, tt, lane);
+#pragma unroll
+    for (int k = 0; k < E; k++) prod[p * N + lane + 32 * k] = csub(mul_shoup(z[k], P.ninv, P.ninvs, Q), Q);
+  }
+}
+int launch_dbg_ntt(const DevConst &P, const u32 *d_a, const u32 *d_b, u32 *d_rt, u32 *d_prod, int npoly, const u32 *d_twl,
+                   void *stream) {
+  if (npoly <= 0) return 0;
+  if (P.N == 1024) dbg_ntt_kernel<10><<<npoly, 32, 0, (cudaStream_t)stream>>>(P, d_a, d_b, d_rt, d_prod, d_twl);
+  else if (P.N == 512) dbg_ntt_kernel<9><<<npoly, 32, 0, (cudaStream_t)stream>>>(P, d_a, d_b, d_rt, d_prod, d_twl);
+  else return (int)cudaErrorInvalidValue;
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// integer-pipe microbenchmark (roofline denominator: measured multiply-class instruction rate)
+// ------------------------------------------------------------------------------------------
+template <int WHICH> __global__ void __launch_bounds__(256) microbench_kernel(u32 *sink, int iters) {
+  constexpr int U = 16;
+  u32 a[U], b = sink[0] | 1u, c = sink[1];
+  u64 wacc[U];
+#pragma unroll
+  for (int i = 0; i < U; i++) { a[i] = threadIdx.x * 2654435761u + i; wacc[i] = a[i]; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < U; i++) {
+      if (WHICH == 0) a[i] = a[i] * b + c;                        // IMAD
+      else if (WHICH == 1) a[i] = __umulhi(a[i], b) + c;          // IMAD.HI
+      else if (WHICH == 2) wacc[i] += (u64)(u32)wacc[i] * b;      // IMAD.WIDE with 64-bit accumulate
+      else if (WHICH == 3) a[i] = min(a[i] + c, a[i] ^ b);        // ALU pipe pair (IADD3 + LOP3 + VIMNMX)
+      else { u32 t = mul_shoup(a[i], b, c, 134215681u); a[i] = a[i] + t; } // Shoup butterfly half
+    }
+  }
+  u32 r = 0;
+#pragma unroll
+  for (int i = 0; i < U; i++) r ^= a[i] ^ (u32)wacc[i] ^ (u32)(wacc[i] >> 32);
+  if (r == 0x12345678u) sink[2] = r;
+}
+int launch_microbench(int which, u32 *d_sink, int iters, int *threads_total, int *ops_per_thread_iter, void *stream) {
+  const int blocks = 148 * 8, threads = 256;
+  *threads_total = blocks * threads;
+  *ops_per_thread_iter = 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (which) {
+  case 0: microbench_kernel<0><<<blocks, threads, 0, st>>>(d_sink, iters); break;
+  case 1: microbench_kernel<1><<<blocks, threads, 0, st>>>(d_sink, iters); break;
+  case 2: microbench_kernel<2><<<blocks, threads, 0, st>>>(d_sink, iters); break;
+  case 3: microbench_kernel<3><<<blocks, threads, 0, st>>>(d_sink, iters); break;
+  default: microbench_kernel<4><<<blocks, threads, 0, st>>>(d_sink, iters); break;
+  }
+  return (int)cudaGetLastError();
+}
+
+} // namespace bfhe

@@ -1,0 +1,141 @@
+"""GPU parity tests proper: every result goes through the C ABI (include/bfhe.h) and is compared
+bit-for-bit with the CPU oracle (oracle/, test infrastructure) on the same serialized keys and inputs."""
+import numpy as np
+import pytest
+
+from conftest import shared_keys
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [("TOY", "GINX"), ("TOY", "AP"), ("STD128_OPT", "GINX")]
+
+
+def _setup(bfhe, orc, ps_name, m_name):
+    ps, m = getattr(bfhe, ps_name), getattr(bfhe, m_name)
+    ctx = shared_keys(bfhe, ps, m, 0)
+    o = orc.Oracle(ps, m)
+    o.import_keys(ctx.export_keys())
+    return ctx, o
+
+
+@pytest.mark.parametrize("ps_name", ["TOY", "STD128_OPT"])
+def test_ntt_roundtrip_and_product(bfhe, orc, ps_name):
+    """a13: INTT(NTT(a)) == a and the negacyclic product equals the oracle's (any slot order gives the same product)."""
+    ctx, o = _setup(bfhe, orc, ps_name, "GINX")
+    rng = np.random.default_rng(7)
+    N, Q = ctx.p.N, ctx.p.Q
+    a = rng.integers(0, Q, size=(16, N), dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, Q, size=(16, N), dtype=np.uint64).astype(np.uint32)
+    a[0] = 0; a[0, 1] = 1          # X
+    a[1] = Q - 1                    # all -1
+    rt, prod = ctx.dbg_ntt_roundtrip(a, b)
+    assert np.array_equal(rt, a)
+    for i in range(a.shape[0]):
+        fa, fb = o.ntt_fwd(a[i]).astype(np.uint64), o.ntt_fwd(b[i]).astype(np.uint64)
+        ref = o.ntt_inv((fa * fb % Q).astype(np.uint32))
+        assert np.array_equal(prod[i], ref), "poly %d" % i
+
+
+def _random_gates(bfhe, rng, n_in, count, ops):
+    g = np.zeros(count, dtype=bfhe.GATE_DTYPE)
+    for i in range(count):
+        a, b = rng.choice(n_in, size=2, replace=False)
+        g[i] = (ops[i % len(ops)], a, b, n_in + i)
+    return g
+
+
+@pytest.mark.parametrize("ps_name,m_name", CONFIGS)
+def test_blind_rotate_accumulator(bfhe, orc, ps_name, m_name):
+    """a9-a12: accumulator after the whole blind rotation, coefficient form, vs the oracle's evaluation-form loop."""
+    ctx, o = _setup(bfhe, orc, ps_name, m_name)
+    rng = np.random.default_rng(3)
+    bits = rng.integers(0, 2, size=6)
+    cts = ctx.encrypt(bits, seed=21)
+    ops = [bfhe.NAND, bfhe.AND | bfhe.NEG1, bfhe.XOR_FAST, bfhe.BOOTSTRAP, bfhe.OR | bfhe.NEG0]
+    gates = _random_gates(bfhe, rng, 6, 5, ops)
+    slab = ctx.slab(6 + 5)
+    slab.upload(cts)
+    acc = ctx.dbg_blind_rotate(slab, gates)
+    for i, g in enumerate(gates):
+        prep = o.prep(int(g["op"]), cts[g["in0"]], cts[g["in1"]])
+        ref = o.blind_rotate(int(g["op"]) & 0xff, prep)
+        assert np.array_equal(acc[i], ref), "gate %d op %x" % (i, g["op"])
+    slab.free()
+
+
+@pytest.mark.parametrize("ps_name,m_name", CONFIGS)
+@pytest.mark.parametrize("gpc", [1, 2, 4])
+def test_bingate_bit_exact(bfhe, orc, ps_name, m_name, gpc):
+    """a7: output LWE ciphertexts of a wavefront are bit-identical to the oracle for every gate type."""
+    ctx, o = _setup(bfhe, orc, ps_name, m_name)
+    rng = np.random.default_rng(100 + gpc)
+    n_in = 8
+    bits = rng.integers(0, 2, size=n_in)
+    cts = ctx.encrypt(bits, seed=33)
+    ops = [bfhe.OR, bfhe.AND, bfhe.NOR, bfhe.NAND, bfhe.XOR_FAST, bfhe.XNOR_FAST, bfhe.XOR, bfhe.XNOR, bfhe.BOOTSTRAP,
+           bfhe.AND | bfhe.NEG0, bfhe.AND | bfhe.NEG1, bfhe.XOR | bfhe.NEG0]
+    count = 13 if ps_name == "TOY" else 9
+    gates = _random_gates(bfhe, rng, n_in, count, ops)
+    ctx.dbg_set_gates_per_cta(gpc)
+    try:
+        out = ctx.eval_bingate_host(gates, cts, count)
+    finally:
+        ctx.dbg_set_gates_per_cta(0)
+    ref = o.new_slab(n_in + count)
+    ref[:n_in] = cts
+    o.eval_gates(gates, ref)
+    w = ctx.p.ct_words
+    assert np.array_equal(out[:, :w], ref[n_in:, :w])
+    # and the decrypted bits equal the plaintext truth table
+    f = {bfhe.OR: lambda a, b: a | b, bfhe.AND: lambda a, b: a & b, bfhe.NOR: lambda a, b: 1 - (a | b),
+         bfhe.NAND: lambda a, b: 1 - (a & b), bfhe.XOR_FAST: lambda a, b: a ^ b, bfhe.XNOR_FAST: lambda a, b: 1 - (a ^ b),
+         bfhe.XOR: lambda a, b: a ^ b, bfhe.XNOR: lambda a, b: 1 - (a ^ b), bfhe.BOOTSTRAP: lambda a, b: a}
+    dec = ctx.decrypt(out)
+    for i, g in enumerate(gates):
+        a, b = int(bits[g["in0"]]), int(bits[g["in1"]])
+        if g["op"] & bfhe.NEG0:
+            a ^= 1
+        if g["op"] & bfhe.NEG1:
+            b ^= 1
+        assert dec[i] == f[int(g["op"]) & 0xff](a, b), "gate %d" % i
+
+
+@pytest.mark.parametrize("ps_name,m_name", CONFIGS)
+def test_not_and_single_gate_api(bfhe, orc, ps_name, m_name):
+    """a6 + the batch-of-one path with the reference's method names (EvalNOT / EvalBinGate / Bootstrap)."""
+    ctx, o = _setup(bfhe, orc, ps_name, m_name)
+    cts = ctx.encrypt([1, 0], seed=5)
+    w = ctx.p.ct_words
+    assert np.array_equal(ctx.EvalNOT(cts[0])[:w], o.eval_not(cts[0])[:w])
+    assert np.array_equal(ctx.EvalBinGate(bfhe.AND, cts[0], cts[1])[:w], o.eval_bingate(orc.AND, cts[0], cts[1])[:w])
+    assert np.array_equal(ctx.Bootstrap(cts[0])[:w], o.bootstrap(cts[0])[:w])
+    # OpenFHE throws on EvalBinGate(ct, ct); the reference catches it at src/gate.cpp:134
+    slab = ctx.slab(2)
+    slab.upload(cts)
+    with pytest.raises(bfhe.BfheError) as e:
+        ctx.eval_bingate_batch(slab, np.array([(bfhe.AND, 0, 0, 1)], dtype=bfhe.GATE_DTYPE))
+    assert e.value.code == bfhe.ERR_ALIAS
+    slab.free()
+
+
+def test_wide_batch_chunks_and_determinism(bfhe, orc):
+    """A batch larger than one tile wave, TOY params: same inputs -> same bits, spot-checked against the oracle."""
+    ctx, o = _setup(bfhe, orc, "TOY", "GINX")
+    rng = np.random.default_rng(9)
+    n_in, count = 64, 700
+    bits = rng.integers(0, 2, size=n_in)
+    cts = ctx.encrypt(bits, seed=77)
+    gates = _random_gates(bfhe, rng, n_in, count, [bfhe.NAND, bfhe.AND, bfhe.XOR])
+    out1 = ctx.eval_bingate_host(gates, cts, count)
+    out2 = ctx.eval_bingate_host(gates, cts, count)
+    assert np.array_equal(out1, out2)
+    ref = o.new_slab(n_in + count)
+    ref[:n_in] = cts
+    sel = np.concatenate([np.arange(0, 40), np.arange(count - 20, count)])
+    o.eval_gates(gates[sel], ref)
+    w = ctx.p.ct_words
+    assert np.array_equal(out1[sel][:, :w], ref[n_in + sel][:, :w])
+    dec = ctx.decrypt(out1)
+    a, b = bits[gates["in0"]], bits[gates["in1"]]
+    exp = np.where(gates["op"] == bfhe.NAND, 1 - (a & b), np.where(gates["op"] == bfhe.AND, a & b, a ^ b))
+    assert np.array_equal(dec, exp)
