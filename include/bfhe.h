@@ -118,6 +118,13 @@ bfhe_circuit *bfhe_circuit_create(bfhe_ctx *);
 void bfhe_circuit_destroy(bfhe_circuit *);
 int bfhe_circuit_read_file(bfhe_circuit *, const char *path);             /* Circuit::ReadFile (.out assembler format) */
 int bfhe_circuit_read_bristol(bfhe_circuit *, const char *path, int new_format); /* analyze+assemble without the text round trip */
+/* netlist from arrays / back to arrays / emitted as the reference's ".out" text.  kind[] uses GateEnum order
+ * {INPUT, OUTPUT, NOT, AND, OR, XOR} (src/gate.h:51); INPUT: in0 = bus, in1 = bit, out = wire; OUTPUT: in0 = wire, out = bit */
+int bfhe_circuit_load_netlist(bfhe_circuit *, const uint8_t *kind, const uint32_t *in0, const uint32_t *in1, const uint32_t *out,
+                              size_t count, uint32_t n_wires, const uint32_t *in_bits, uint32_t n_in_buses, uint32_t out_bits);
+int bfhe_circuit_get_netlist(const bfhe_circuit *, uint8_t *kind, uint32_t *in0, uint32_t *in1, uint32_t *out, size_t cap,
+                             uint32_t *count, uint32_t *n_wires);
+int bfhe_circuit_write_out(const bfhe_circuit *, const char *path);
 int bfhe_circuit_set_flags(bfhe_circuit *, int plaintext, int encrypted, int verify); /* setPlaintext/Encrypted/Verify */
 int bfhe_circuit_info(const bfhe_circuit *, uint32_t *n_inputs, uint32_t *input_bits /*[8]*/, uint32_t *n_output_bits,
                       uint32_t *n_gates, uint32_t *n_bootstraps, uint32_t *n_levels, uint32_t *max_width);
@@ -131,6 +138,12 @@ int bfhe_circuit_stats(const bfhe_circuit *, double *device_ms, double *host_ms,
 /* per-level plan, for tests of the sharding logic: gates of level L assigned to `rank` of `world` */
 int bfhe_circuit_level_plan(const bfhe_circuit *, uint32_t level, int rank, int world, bfhe_gate *out, size_t cap,
                             uint32_t *count, uint32_t *first_row, uint32_t *rows_per_rank);
+/* plan internals for tests: total slab rows, first fresh-encryption row, level count incl. the input-bootstrap
+ * level 0, slab row of every output bit (bit 31 set = read through NOT), and the EvalNOT pairs of one level */
+int bfhe_circuit_plan_misc(const bfhe_circuit *, uint32_t *total_rows, uint32_t *fresh_base, uint32_t *n_levels_incl_input,
+                           uint32_t *out_rows, uint32_t *not_count, uint32_t level, uint32_t *not_pairs);
+int bfhe_circuit_use_graph(bfhe_circuit *, int on); /* one CUDA graph per circuit instead of per-level launches (default on) */
+int bfhe_circuit_download_slab(bfhe_circuit *, uint32_t *host, size_t rows_cap); /* every wire ciphertext, for parity tests */
 int bfhe_circuit_dump_gate_count(const bfhe_circuit *, uint32_t *in, uint32_t *out, uint32_t *and_, uint32_t *or_,
                                  uint32_t *xor_, uint32_t *not_);
 

@@ -45,6 +45,11 @@ ABI_SYMBOLS = [
     "bfhe_slab_download", "bfhe_eval_not_batch", "bfhe_eval_bingate_batch", "bfhe_bootstrap_batch",
     "bfhe_eval_bingate_host", "bfhe_profile_enable", "bfhe_profile_read", "bfhe_microbench_int",
     "bfhe_dbg_ntt_roundtrip", "bfhe_dbg_blind_rotate", "bfhe_dbg_set_gates_per_cta",
+    "bfhe_circuit_create", "bfhe_circuit_destroy", "bfhe_circuit_read_file", "bfhe_circuit_read_bristol",
+    "bfhe_circuit_set_flags", "bfhe_circuit_info", "bfhe_circuit_set_sharding", "bfhe_get_nccl_unique_id",
+    "bfhe_circuit_reset", "bfhe_circuit_set_input", "bfhe_circuit_clock", "bfhe_circuit_stats",
+    "bfhe_circuit_level_plan", "bfhe_circuit_plan_misc", "bfhe_circuit_use_graph", "bfhe_circuit_download_slab",
+    "bfhe_circuit_dump_gate_count", "bfhe_circuit_load_netlist", "bfhe_circuit_get_netlist", "bfhe_circuit_write_out",
 ]
 
 _lib = None
@@ -91,6 +96,28 @@ def lib():
     L.bfhe_dbg_ntt_roundtrip.argtypes = [vp, vp, sz, vp, vp, vp]
     L.bfhe_dbg_blind_rotate.argtypes = [vp, vp, vp, sz, vp]
     L.bfhe_dbg_set_gates_per_cta.argtypes = [vp, C.c_int]
+    L.bfhe_circuit_create.restype = vp
+    L.bfhe_circuit_create.argtypes = [vp]
+    L.bfhe_circuit_destroy.restype = None
+    L.bfhe_circuit_destroy.argtypes = [vp]
+    L.bfhe_circuit_read_file.argtypes = [vp, C.c_char_p]
+    L.bfhe_circuit_read_bristol.argtypes = [vp, C.c_char_p, C.c_int]
+    L.bfhe_circuit_set_flags.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.bfhe_circuit_info.argtypes = [vp, u32p, u32p, u32p, u32p, u32p, u32p, u32p]
+    L.bfhe_circuit_set_sharding.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.bfhe_get_nccl_unique_id.argtypes = [vp]
+    L.bfhe_circuit_reset.argtypes = [vp]
+    L.bfhe_circuit_set_input.argtypes = [vp, vp, sz, C.c_uint64]
+    L.bfhe_circuit_clock.argtypes = [vp, vp, sz, vp]
+    L.bfhe_circuit_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.bfhe_circuit_level_plan.argtypes = [vp, C.c_uint32, C.c_int, C.c_int, vp, sz, u32p, u32p, u32p]
+    L.bfhe_circuit_plan_misc.argtypes = [vp, u32p, u32p, u32p, vp, u32p, C.c_uint32, vp]
+    L.bfhe_circuit_use_graph.argtypes = [vp, C.c_int]
+    L.bfhe_circuit_download_slab.argtypes = [vp, vp, sz]
+    L.bfhe_circuit_dump_gate_count.argtypes = [vp, u32p, u32p, u32p, u32p, u32p, u32p]
+    L.bfhe_circuit_load_netlist.argtypes = [vp, vp, vp, vp, vp, sz, C.c_uint32, vp, C.c_uint32, C.c_uint32]
+    L.bfhe_circuit_get_netlist.argtypes = [vp, vp, vp, vp, vp, sz, u32p, u32p]
+    L.bfhe_circuit_write_out.argtypes = [vp, C.c_char_p]
     _lib = L
     return L
 
@@ -279,3 +306,162 @@ class Context:
 
     def dbg_set_gates_per_cta(self, g):
         self._ck(self.L.bfhe_dbg_set_gates_per_cta(self.h, g))
+
+
+def nccl_unique_id():
+    buf = np.zeros(128, dtype=np.uint8)
+    rc = lib().bfhe_get_nccl_unique_id(buf.ctypes.data)
+    if rc:
+        raise BfheError(rc, lib().bfhe_last_error().decode())
+    return buf
+
+
+class Circuit:
+    """Mirror of the reference's ``class Circuit`` (src/circuit.h:56-72): ReadFile / Reset / SetInput / Clock /
+    set{Plaintext,Encrypted,Verify} / dumpGateCount, evaluated level-synchronously on the GPU."""
+
+    def __init__(self, ctx):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = self.L.bfhe_circuit_create(ctx.h)
+        self._flags = [False, False, False]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.bfhe_circuit_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        self.ctx._ck(rc)
+
+    def ReadFile(self, path):
+        self._ck(self.L.bfhe_circuit_read_file(self.h, str(path).encode()))
+        return True
+
+    def ReadBristol(self, path, new_format=False):
+        self._ck(self.L.bfhe_circuit_read_bristol(self.h, str(path).encode(), int(new_format)))
+        return True
+
+    def load_netlist(self, kind, in0, in1, out, n_wires, in_bits, out_bits):
+        kind = np.ascontiguousarray(kind, dtype=np.uint8)
+        in0, in1, out = (np.ascontiguousarray(a, dtype=np.uint32) for a in (in0, in1, out))
+        ib = np.ascontiguousarray(in_bits, dtype=np.uint32)
+        self._ck(self.L.bfhe_circuit_load_netlist(self.h, _ptr(kind), _ptr(in0), _ptr(in1), _ptr(out), kind.size, int(n_wires),
+                                                  _ptr(ib), ib.size, int(out_bits)))
+
+    def load_npz(self, path):
+        d = np.load(path)
+        self.load_netlist(d["kind"], d["in0"], d["in1"], d["out"], int(d["n_wires"]), d["in_bits"], int(d["out_bits"]))
+
+    def get_netlist(self):
+        cnt, nw = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.bfhe_circuit_get_netlist(self.h, None, None, None, None, 0, C.byref(cnt), C.byref(nw)))
+        kind = np.zeros(cnt.value, dtype=np.uint8)
+        in0, in1, out = (np.zeros(cnt.value, dtype=np.uint32) for _ in range(3))
+        self._ck(self.L.bfhe_circuit_get_netlist(self.h, _ptr(kind), _ptr(in0), _ptr(in1), _ptr(out), cnt.value, C.byref(cnt),
+                                                 C.byref(nw)))
+        i = self.info()
+        return dict(kind=kind, in0=in0, in1=in1, out=out, n_wires=nw.value, in_bits=np.array(i["input_bits"], dtype=np.uint32),
+                    out_bits=i["output_bits"])
+
+    def write_out(self, path):
+        self._ck(self.L.bfhe_circuit_write_out(self.h, str(path).encode()))
+
+    def info(self):
+        v = [C.c_uint32() for _ in range(6)]
+        bits = (C.c_uint32 * 8)()
+        self._ck(self.L.bfhe_circuit_info(self.h, C.byref(v[0]), bits, C.byref(v[1]), C.byref(v[2]), C.byref(v[3]),
+                                          C.byref(v[4]), C.byref(v[5])))
+        return dict(n_inputs=v[0].value, input_bits=list(bits)[: v[0].value], output_bits=v[1].value, gates=v[2].value,
+                    bootstraps=v[3].value, levels=v[4].value, max_width=v[5].value)
+
+    def dumpGateCount(self):
+        v = [C.c_uint32() for _ in range(6)]
+        self._ck(self.L.bfhe_circuit_dump_gate_count(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("input", "output", "and", "or", "xor", "not"), [x.value for x in v]))
+
+    def _push_flags(self):
+        self._ck(self.L.bfhe_circuit_set_flags(self.h, *[int(f) for f in self._flags]))
+
+    def setPlaintext(self, f):
+        self._flags[0] = bool(f)
+        self._push_flags()
+
+    def setEncrypted(self, f):
+        self._flags[1] = bool(f)
+        self._push_flags()
+
+    def setVerify(self, f):
+        self._flags[2] = bool(f)
+        if f:  # src/circuit.cpp:833-840
+            self._flags[0] = self._flags[1] = True
+        self._push_flags()
+
+    def getPlaintext(self):
+        return self._flags[0]
+
+    def getEncrypted(self):
+        return self._flags[1]
+
+    def getVerify(self):
+        return self._flags[2]
+
+    def Reset(self):
+        self._flags = [False, False, False]  # src/circuit.cpp:378-381
+        self._push_flags()
+        self._ck(self.L.bfhe_circuit_reset(self.h))
+
+    def set_sharding(self, rank, world, unique_id=None):
+        self._ck(self.L.bfhe_circuit_set_sharding(self.h, rank, world, _ptr(unique_id)))
+
+    def use_graph(self, on):
+        self._ck(self.L.bfhe_circuit_use_graph(self.h, int(on)))
+
+    def SetInput(self, inputs, verbose=False, seed=0):
+        """inputs: list of bit lists, one per input bus (Inputs = vector<vector<unsigned>>, src/circuit.h:50)."""
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(i, dtype=np.uint8).ravel() for i in inputs]), dtype=np.uint8)
+        self._ck(self.L.bfhe_circuit_set_input(self.h, _ptr(flat), flat.size, seed))
+
+    def Clock(self):
+        """returns Outputs = [[bits of OUT:0]]; the plaintext pass result is kept in self.plain_out"""
+        n = self.info()["output_bits"]
+        out = np.zeros(n, dtype=np.uint8)
+        pout = np.zeros(n, dtype=np.uint8)
+        self._ck(self.L.bfhe_circuit_clock(self.h, _ptr(out), n, _ptr(pout)))
+        self.plain_out = [pout.tolist()]
+        if self._flags[1]:
+            return [out.tolist()]
+        return [pout.tolist()]
+
+    def stats(self):
+        d, h, m = C.c_double(), C.c_double(), C.c_uint64()
+        self._ck(self.L.bfhe_circuit_stats(self.h, C.byref(d), C.byref(h), C.byref(m)))
+        return dict(device_ms=d.value, host_ms=h.value, verify_mismatches=m.value)
+
+    def level_plan(self, level, rank, world):
+        cnt, first, rpr = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._ck(self.L.bfhe_circuit_level_plan(self.h, level, rank, world, None, 0, C.byref(cnt), C.byref(first), C.byref(rpr)))
+        g = np.zeros(cnt.value, dtype=GATE_DTYPE)
+        self._ck(self.L.bfhe_circuit_level_plan(self.h, level, rank, world, _ptr(g), g.size, C.byref(cnt), C.byref(first),
+                                                C.byref(rpr)))
+        return g, first.value, rpr.value
+
+    def plan_misc(self, level=0):
+        tot, fresh, nl, nc = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        outs = np.zeros(self.info()["output_bits"], dtype=np.uint32)
+        self._ck(self.L.bfhe_circuit_plan_misc(self.h, C.byref(tot), C.byref(fresh), C.byref(nl), _ptr(outs), C.byref(nc), level, None))
+        pairs = np.zeros((nc.value, 2), dtype=np.uint32)
+        if nc.value:
+            self._ck(self.L.bfhe_circuit_plan_misc(self.h, None, None, None, None, C.byref(nc), level, _ptr(pairs)))
+        return dict(total_rows=tot.value, fresh_base=fresh.value, n_levels=nl.value, out_rows=outs, nots=pairs)
+
+    def download_slab(self):
+        rows = self.plan_misc()["total_rows"]
+        out = np.zeros((rows, self.ctx.stride), dtype=np.uint32)
+        self._ck(self.L.bfhe_circuit_download_slab(self.h, _ptr(out), rows))
+        return out

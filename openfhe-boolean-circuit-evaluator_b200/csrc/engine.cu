@@ -599,7 +599,9 @@ static int eval_batch_locked(bfhe_ctx *c, uint32_t *slab, const bfhe_gate *gates
   for (size_t i = 0; i < count; i++) {
     const u32 g = gates[i].op & 0xff;
     if (g > BFHE_BOOTSTRAP) { set_error("unknown gate type"); return BFHE_ERR_ARG; }
-    if (g != BFHE_BOOTSTRAP && gates[i].in0 == gates[i].in1) {
+    // a and NOT(a) are distinct ciphertext objects for OpenFHE; only the very same ciphertext twice is rejected
+    if (g != BFHE_BOOTSTRAP && gates[i].in0 == gates[i].in1 &&
+        (((gates[i].op & BFHE_NEG0) != 0) == ((gates[i].op & BFHE_NEG1) != 0))) {
       set_error("EvalBinGate: please only use independent ciphertexts as inputs (gate " + std::to_string(i) + ")");
       return BFHE_ERR_ALIAS;
     }

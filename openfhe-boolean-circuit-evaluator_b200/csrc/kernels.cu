@@ -20,6 +20,7 @@
 //  * A CTA carries G gates through the n blind-rotation steps in lock step so that every
 //    bootstrapping-key word loaded from L2 is reused G times from registers (GINX).
 #include "common.hpp"
+#include <algorithm>
 #include <cuda_runtime.h>
 
 namespace bfhe {
@@ -461,6 +462,7 @@ static int launch_br_inst(const DevConst &P, const DevGate *d_gates, int count, 
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
+  if (count <= 0) return 0; // attribute warm-up only
   const int ctas = (count + G - 1) / G;
   if (info) { info->gates_per_cta = G; info->ctas = ctas; info->smem_bytes = Cfg::smem_bytes; }
   kern<<<ctas, Cfg::THREADS, Cfg::smem_bytes, st>>>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc);
@@ -475,6 +477,23 @@ static int launch_br_g(int G, const DevConst &P, const DevGate *d_gates, int cou
   case 2: return launch_br_inst<LOGN, DG, LOGBG, 2, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
   default: return launch_br_inst<LOGN, DG, LOGBG, 4, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
   }
+}
+
+template <int LOGN, int DG, int LOGBG> static int br_attrs() {
+  DevConst P{};
+  int rc = 0;
+  for (int G : {1, 2, 4}) {
+    rc |= launch_br_g<LOGN, DG, LOGBG, false>(G, P, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+    rc |= launch_br_g<LOGN, DG, LOGBG, true>(G, P, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+  }
+  return rc;
+}
+static int keyswitch_attrs();
+int blind_rotate_set_attrs() {
+  int rc = br_attrs<10, 4, 7>();
+  rc |= br_attrs<9, 3, 9>();
+  rc |= keyswitch_attrs();
+  return rc;
 }
 
 int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates, int count, const u32 *d_bk, const u32 *d_twl,
@@ -559,6 +578,11 @@ __global__ void __launch_bounds__(COLS *RG) keyswitch_kernel(const __grid_consta
   }
 }
 
+static int keyswitch_attrs() {
+  constexpr int COLS = 256, RG = 4;
+  const size_t smem = (size_t)(2048 + 2) * 4 + (size_t)RG * COLS * 2 * 8;
+  return (int)cudaFuncSetAttribute(keyswitch_kernel<true, COLS, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+}
 int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates, int count, const void *d_ksk, int elem_bytes,
                      void *stream) {
   if (count <= 0) return 0;
@@ -569,7 +593,7 @@ int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates
     const int rowlen_words = 256; // 512 uint16 per row
     size_t smem = (size_t)((nrows + 1) & ~1) * 4 + (size_t)RG * COLS * 2 * 8;
     static bool done = false;
-    if (!done) { cudaFuncSetAttribute(keyswitch_kernel<true, COLS, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done = true; }
+    if (!done) { keyswitch_attrs(); done = true; }
     keyswitch_kernel<true, COLS, RG><<<count, COLS * RG, smem, st>>>(P, d_ext, d_gates, d_ksk, rowlen_words);
   } else {
     constexpr int COLS = 128, RG = 4;

@@ -1,0 +1,765 @@
+// circuit.cpp -- level-synchronous circuit evaluator behind the reference's Circuit API.
+//
+// Replaces Circuit::{ReadFile,Reset,SetInput,Clock} + _CircuitManager/_ExecuteGates
+// (src/circuit.cpp:102-817 in /root/reference).  The reference's dataflow manager fires gate g in wave
+// 1 + max(wave of producers), i.e. ASAP levelisation; here the levels are computed once,
+// and each bootstrap (sub-)level is ONE batched launch of the blind-rotation and key-switch kernels
+// instead of one OpenMP task per gate.  XOR is the reference's composite OR(AND(a,!b), AND(!a,b))
+// (src/gate.cpp:198-202): two ANDs at level L, the OR at level L+1.  NOT costs no bootstrap and is folded
+// into the consumer's operand flags; NOT outputs are only materialised where a ciphertext is needed
+// (circuit outputs, verify mode).
+//
+// Multi-GPU: every level's gate list is block-partitioned over the ranks, keys and the wire slab are
+// replicated, and the level's output rows are exchanged with one in-place ncclAllGather.
+#include "../csrc/engine.hpp"
+#include "netlist.hpp"
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+
+using namespace bfhe;
+
+namespace {
+
+// ---- minimal NCCL binding, resolved at run time so that CPU-only use needs no NCCL ----
+struct Id128 { char b[128]; }; // ncclUniqueId is passed by value
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool load_nccl() {
+  if (g_nccl.h) return true;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { set_error(std::string("cannot load NCCL: ") + dlerror()); return false; }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+    set_error("NCCL symbols missing");
+    return false;
+  }
+  g_nccl.h = h;
+  return true;
+}
+constexpr int NCCL_UINT32 = 3;
+
+struct NotOp { uint32_t in_row, out_row; };
+struct Level {
+  std::vector<bfhe_gate> gates; // out rows are first_row + index
+  uint32_t first_row = 0;
+  std::vector<NotOp> nots;      // materialised after this level
+};
+
+} // namespace
+
+struct bfhe_circuit {
+  bfhe_ctx *ctx = nullptr;
+  Netlist nl;
+  bool loaded = false;
+  bool plaintext = false, encrypted = false, verify = false;
+  int rank = 0, world = 1;
+  void *comm = nullptr;
+
+  // plan
+  bool planned = false;
+  std::vector<uint32_t> topo;        // gate indices in dependency order
+  std::vector<uint32_t> wire_row;    // slab row holding the wire (possibly of its un-negated source)
+  std::vector<uint8_t> wire_neg;     // wire = NOT^neg(row)
+  std::vector<uint32_t> wire_level;
+  std::vector<Level> levels;         // levels[0] = Bootstrap of the fresh input encryptions
+  std::vector<uint32_t> level_rpr;   // rows per rank
+  uint32_t total_rows = 0, fresh_base = 0, n_in = 0;
+  std::vector<uint32_t> in_wire_of_bit; // concatenated input bit -> wire
+  std::vector<uint32_t> out_wire;       // output bit -> wire
+  uint32_t n_bootstraps = 0, max_width = 0;
+
+  // device state
+  uint32_t *slab = nullptr;
+  DevGate *d_desc = nullptr;             // my slice of every level, concatenated
+  std::vector<size_t> desc_off;          // per level
+  std::vector<uint32_t> my_count;        // per level
+  const u32 **d_not_in = nullptr;
+  u32 **d_not_out = nullptr;
+  std::vector<size_t> not_off;
+  u32 *d_ext = nullptr;
+  size_t ext_cap = 0;
+  bool dev_ready = false;
+  cudaGraphExec_t graph = nullptr;
+  bool use_graph = true;
+
+  // values
+  std::vector<uint8_t> in_bits_set, plain_wire;
+  bool has_input = false, done = false;
+  double device_ms = 0, host_ms = 0;
+  uint64_t verify_mismatches = 0, verify_checked = 0;
+};
+
+static void free_device(bfhe_circuit *c) {
+  if (c->ctx && c->ctx->device >= 0) {
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    if (c->graph) cudaGraphExecDestroy(c->graph);
+    cudaFree(c->slab); cudaFree(c->d_desc); cudaFree(c->d_not_in); cudaFree(c->d_not_out); cudaFree(c->d_ext);
+  }
+  c->graph = nullptr; c->slab = nullptr; c->d_desc = nullptr; c->d_not_in = nullptr; c->d_not_out = nullptr; c->d_ext = nullptr;
+  c->dev_ready = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// planning
+// ---------------------------------------------------------------------------------------------
+static int build_plan(bfhe_circuit *c) {
+  const Netlist &nl = c->nl;
+  const uint32_t NW = nl.n_wires, NG = (uint32_t)nl.gates.size();
+  const uint32_t NONE = 0xffffffffu;
+  std::vector<uint32_t> producer(NW, NONE);
+  for (uint32_t i = 0; i < NG; i++) {
+    const NetGate &g = nl.gates[i];
+    if (g.kind == GateKind::OUTPUT) continue;
+    if (g.out >= NW) { set_error("wire id out of range"); return BFHE_ERR_FORMAT; }
+    if (producer[g.out] != NONE) { set_error("wire driven twice"); return BFHE_ERR_FORMAT; }
+    producer[g.out] = i;
+  }
+  // dependency order (the reference needs none: its manager is dataflow-driven; files are ordered anyway)
+  c->topo.clear();
+  c->topo.reserve(NG);
+  {
+    std::vector<uint8_t> state(NG, 0);
+    std::vector<uint32_t> stack;
+    auto deps = [&](const NetGate &g, uint32_t d[2]) -> int {
+      switch (g.kind) {
+      case GateKind::INPUT: return 0;
+      case GateKind::OUTPUT: case GateKind::NOT: d[0] = g.in0; return 1;
+      default: d[0] = g.in0; d[1] = g.in1; return 2;
+      }
+    };
+    for (uint32_t s = 0; s < NG; s++) {
+      if (state[s]) continue;
+      stack.push_back(s);
+      while (!stack.empty()) {
+        uint32_t gi = stack.back();
+        if (state[gi] == 2) { stack.pop_back(); continue; }
+        uint32_t d[2];
+        int nd = deps(nl.gates[gi], d);
+        bool ready = true;
+        for (int k = 0; k < nd; k++) {
+          if (d[k] >= NW || producer[d[k]] == NONE) { set_error("gate reads an undriven wire"); return BFHE_ERR_FORMAT; }
+          uint32_t p = producer[d[k]];
+          if (state[p] == 1) { set_error("combinational loop in netlist"); return BFHE_ERR_FORMAT; }
+          if (state[p] == 0) { ready = false; stack.push_back(p); }
+        }
+        if (!ready) { state[gi] = 1; continue; }
+        state[gi] = 2;
+        c->topo.push_back(gi);
+        stack.pop_back();
+      }
+    }
+  }
+  // which wires need a ciphertext of their own even though they are a NOT of something
+  std::vector<uint8_t> feeds_output(NW, 0);
+  for (const NetGate &g : nl.gates)
+    if (g.kind == GateKind::OUTPUT) feeds_output[g.in0] = 1;
+
+  c->n_in = 0;
+  for (auto b : nl.in_bits) c->n_in += b;
+  std::vector<uint32_t> bus_base(nl.in_bits.size() + 1, 0);
+  for (size_t b = 0; b < nl.in_bits.size(); b++) bus_base[b + 1] = bus_base[b] + nl.in_bits[b];
+  c->in_wire_of_bit.assign(c->n_in, NONE);
+  c->out_wire.assign(nl.out_bits, NONE);
+  c->wire_row.assign(NW, NONE);
+  c->wire_neg.assign(NW, 0);
+  c->wire_level.assign(NW, 0);
+
+  // pass 1: levels.  Rows are assigned afterwards, so gates carry (level, index) first.
+  struct Pending { uint32_t gate; uint32_t level; };
+  std::vector<std::vector<uint32_t>> lvl_gates(1); // netlist gate ids per bootstrap level (XOR appears at L and L+1)
+  struct Slot { uint32_t level, index; };
+  std::vector<Slot> wire_slot(NW, Slot{NONE, NONE}); // for bootstrapped wires
+  std::vector<Slot> xor_t1(NG, Slot{NONE, NONE});
+  std::vector<std::vector<uint32_t>> lvl_nots(1);    // materialised NOT gate ids per level
+  auto ensure_level = [&](uint32_t L) { if (lvl_gates.size() <= L) { lvl_gates.resize(L + 1); lvl_nots.resize(L + 1); } };
+  // level-0 "gates": Bootstrap(fresh input i) -> row i
+  for (uint32_t gi : c->topo) {
+    const NetGate &g = nl.gates[gi];
+    switch (g.kind) {
+    case GateKind::INPUT: {
+      if (g.in0 >= nl.in_bits.size() || g.in1 >= nl.in_bits[g.in0]) { set_error("LOAD out of range"); return BFHE_ERR_FORMAT; }
+      uint32_t bit = bus_base[g.in0] + g.in1;
+      if (c->in_wire_of_bit[bit] != NONE) { set_error("input bit loaded twice"); return BFHE_ERR_FORMAT; }
+      c->in_wire_of_bit[bit] = g.out;
+      c->wire_level[g.out] = 0;
+      wire_slot[g.out] = Slot{0, bit};
+      break;
+    }
+    case GateKind::NOT: {
+      c->wire_level[g.out] = c->wire_level[g.in0];
+      if (c->verify || feeds_output[g.out]) lvl_nots[c->wire_level[g.in0]].push_back(gi);
+      break;
+    }
+    case GateKind::AND: case GateKind::OR: case GateKind::XOR: {
+      uint32_t L = 1 + std::max(c->wire_level[g.in0], c->wire_level[g.in1]);
+      ensure_level(L + (g.kind == GateKind::XOR ? 1 : 0));
+      if (g.kind == GateKind::XOR) {
+        xor_t1[gi] = Slot{L, (uint32_t)lvl_gates[L].size()};
+        lvl_gates[L].push_back(gi);      // AND(a,!b)
+        lvl_gates[L].push_back(gi);      // AND(!a,b)
+        wire_slot[g.out] = Slot{L + 1, (uint32_t)lvl_gates[L + 1].size()};
+        lvl_gates[L + 1].push_back(gi);  // OR
+        c->wire_level[g.out] = L + 1;
+      } else {
+        wire_slot[g.out] = Slot{L, (uint32_t)lvl_gates[L].size()};
+        lvl_gates[L].push_back(gi);
+        c->wire_level[g.out] = L;
+      }
+      break;
+    }
+    case GateKind::OUTPUT:
+      if (g.out >= nl.out_bits) { set_error("STORE out of range"); return BFHE_ERR_FORMAT; }
+      c->out_wire[g.out] = g.in0;
+      break;
+    }
+  }
+  for (uint32_t b = 0; b < c->n_in; b++)
+    if (c->in_wire_of_bit[b] == NONE) { set_error("input bit " + std::to_string(b) + " is never loaded"); return BFHE_ERR_FORMAT; }
+  for (uint32_t b = 0; b < nl.out_bits; b++)
+    if (c->out_wire[b] == NONE) { set_error("output bit " + std::to_string(b) + " is never stored"); return BFHE_ERR_FORMAT; }
+
+  // pass 2: rows.  level block = [bootstrap outputs, padded to world * rows_per_rank][materialised NOTs]
+  const uint32_t NL = (uint32_t)lvl_gates.size();
+  c->levels.assign(NL, Level());
+  c->level_rpr.assign(NL, 0);
+  std::vector<uint32_t> first(NL, 0);
+  uint32_t row = 0;
+  std::vector<std::vector<uint32_t>> not_rows(NL);
+  c->max_width = 0;
+  c->n_bootstraps = 0;
+  for (uint32_t L = 0; L < NL; L++) {
+    const uint32_t cnt = (L == 0) ? c->n_in : (uint32_t)lvl_gates[L].size();
+    const uint32_t rpr = (cnt + c->world - 1) / c->world;
+    first[L] = row;
+    c->level_rpr[L] = rpr;
+    row += rpr * c->world;
+    not_rows[L].resize(lvl_nots[L].size());
+    for (auto &r : not_rows[L]) r = row++;
+    if (L > 0) { c->max_width = std::max(c->max_width, cnt); c->n_bootstraps += cnt; }
+  }
+  c->fresh_base = row;
+  row += c->n_in;
+  c->total_rows = row;
+  // wire -> (row, neg) in dependency order; NOT chains fold into the flag
+  std::vector<uint32_t> not_cursor(NL, 0);
+  for (uint32_t gi : c->topo) {
+    const NetGate &g = nl.gates[gi];
+    if (g.kind == GateKind::OUTPUT) continue;
+    if (g.kind == GateKind::NOT) {
+      const uint32_t L = c->wire_level[g.in0];
+      if (c->verify || feeds_output[g.out]) {
+        // materialise from the source row with the right polarity: NOT is an involution, so
+        // out = NOT(row) if the input wire is un-negated; if the input is itself a folded NOT the
+        // output equals the source row, and a fresh copy is not needed
+        if (c->wire_neg[g.in0]) {
+          c->wire_row[g.out] = c->wire_row[g.in0];
+          c->wire_neg[g.out] = 0;
+          not_rows[L][not_cursor[L]++] = NONE;
+        } else {
+          c->wire_row[g.out] = not_rows[L][not_cursor[L]++];
+          c->wire_neg[g.out] = 0;
+        }
+      } else {
+        c->wire_row[g.out] = c->wire_row[g.in0];
+        c->wire_neg[g.out] = c->wire_neg[g.in0] ^ 1;
+      }
+      continue;
+    }
+    const Slot s = wire_slot[g.out];
+    c->wire_row[g.out] = first[s.level] + s.index;
+    c->wire_neg[g.out] = 0;
+  }
+  // gate descriptors
+  for (uint32_t L = 0; L < NL; L++) {
+    Level &lv = c->levels[L];
+    lv.first_row = first[L];
+    if (L == 0) {
+      for (uint32_t b = 0; b < c->n_in; b++) lv.gates.push_back(bfhe_gate{BFHE_BOOTSTRAP, c->fresh_base + b, c->fresh_base + b, b});
+    } else {
+      std::vector<uint8_t> seen_xor_first;
+      for (uint32_t idx = 0; idx < lvl_gates[L].size(); idx++) {
+        const uint32_t gi = lvl_gates[L][idx];
+        const NetGate &g = nl.gates[gi];
+        const uint32_t out = first[L] + idx;
+        const uint32_t ra = c->wire_row[g.in0], rb = c->wire_row[g.in1];
+        const uint32_t fa = c->wire_neg[g.in0] ? BFHE_NEG0 : 0, fb = c->wire_neg[g.in1] ? BFHE_NEG1 : 0;
+        if (g.kind == GateKind::XOR) {
+          const Slot t1 = xor_t1[gi];
+          if (t1.level == L) { // the two ANDs; idx - t1.index is 0 or 1
+            if (idx == t1.index) lv.gates.push_back(bfhe_gate{BFHE_AND | fa | (fb ^ BFHE_NEG1), ra, rb, out});
+            else lv.gates.push_back(bfhe_gate{BFHE_AND | (fa ^ BFHE_NEG0) | fb, ra, rb, out});
+          } else {
+            lv.gates.push_back(bfhe_gate{BFHE_OR, first[t1.level] + t1.index, first[t1.level] + t1.index + 1, out});
+          }
+        } else {
+          lv.gates.push_back(bfhe_gate{(g.kind == GateKind::AND ? (uint32_t)BFHE_AND : (uint32_t)BFHE_OR) | fa | fb, ra, rb, out});
+        }
+        const bfhe_gate &d = lv.gates.back();
+        if (d.in0 == d.in1 && (((d.op & BFHE_NEG0) != 0) == ((d.op & BFHE_NEG1) != 0))) {
+          // OpenFHE throws for EvalBinGate(ct, ct); the reference's catch re-encrypts both inputs with the
+          // secret key (src/gate.cpp:134-152).  A server-side evaluator has no secret key: reject at load.
+          set_error("gate with both inputs on the same wire (EvalBinGate requires independent ciphertexts)");
+          return BFHE_ERR_ALIAS;
+        }
+      }
+    }
+    for (size_t k = 0; k < lvl_nots[L].size(); k++) {
+      if (not_rows[L][k] == NONE) continue;
+      const NetGate &g = nl.gates[lvl_nots[L][k]];
+      lv.nots.push_back(NotOp{c->wire_row[g.in0], not_rows[L][k]});
+    }
+  }
+  c->planned = true;
+  return BFHE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device plan
+// ---------------------------------------------------------------------------------------------
+static void my_slice(const bfhe_circuit *c, uint32_t L, int rank, uint32_t *begin, uint32_t *count) {
+  const uint32_t cnt = (uint32_t)c->levels[L].gates.size(), rpr = c->level_rpr[L];
+  const uint32_t b = std::min(cnt, rpr * (uint32_t)rank), e = std::min(cnt, rpr * (uint32_t)(rank + 1));
+  *begin = b;
+  *count = e - b;
+}
+
+static int upload_plan(bfhe_circuit *c) {
+  bfhe_ctx *x = c->ctx;
+  if (x->device < 0) { set_error("no CUDA device attached (this engine has no CPU fallback)"); return BFHE_ERR_CUDA; }
+  int rc = ensure_device_keys(x);
+  if (rc) return rc;
+  rc = blind_rotate_set_attrs(); // function attributes must not be set under stream capture
+  if (rc) return cuda_fail((cudaError_t)rc, "cudaFuncSetAttribute");
+  free_device(c);
+  const size_t st = x->p.ct_stride;
+  BFHE_CUDA(cudaMalloc(&c->slab, (size_t)c->total_rows * st * 4));
+  BFHE_CUDA(cudaMemset(c->slab, 0, (size_t)c->total_rows * st * 4));
+  std::vector<DevGate> desc;
+  std::vector<const u32 *> nin;
+  std::vector<u32 *> nout;
+  c->desc_off.clear(); c->my_count.clear(); c->not_off.clear();
+  uint32_t widest = 1;
+  for (uint32_t L = 0; L < c->levels.size(); L++) {
+    uint32_t b, n;
+    my_slice(c, L, c->rank, &b, &n);
+    c->desc_off.push_back(desc.size());
+    c->my_count.push_back(n);
+    widest = std::max(widest, n);
+    for (uint32_t i = b; i < b + n; i++) {
+      const bfhe_gate &g = c->levels[L].gates[i];
+      desc.push_back(DevGate{c->slab + (size_t)g.in0 * st, c->slab + (size_t)g.in1 * st, c->slab + (size_t)g.out * st, g.op, 0});
+    }
+    c->not_off.push_back(nin.size());
+    for (const NotOp &o : c->levels[L].nots) { nin.push_back(c->slab + (size_t)o.in_row * st); nout.push_back(c->slab + (size_t)o.out_row * st); }
+  }
+  c->not_off.push_back(nin.size());
+  BFHE_CUDA(cudaMalloc(&c->d_desc, std::max<size_t>(desc.size(), 1) * sizeof(DevGate)));
+  BFHE_CUDA(cudaMemcpy(c->d_desc, desc.data(), desc.size() * sizeof(DevGate), cudaMemcpyHostToDevice));
+  BFHE_CUDA(cudaMalloc(&c->d_not_in, std::max<size_t>(nin.size(), 1) * sizeof(void *)));
+  BFHE_CUDA(cudaMalloc(&c->d_not_out, std::max<size_t>(nin.size(), 1) * sizeof(void *)));
+  BFHE_CUDA(cudaMemcpy(c->d_not_in, nin.data(), nin.size() * sizeof(void *), cudaMemcpyHostToDevice));
+  BFHE_CUDA(cudaMemcpy(c->d_not_out, nout.data(), nout.size() * sizeof(void *), cudaMemcpyHostToDevice));
+  c->ext_cap = widest;
+  BFHE_CUDA(cudaMalloc(&c->d_ext, (size_t)widest * (x->p.N + 4) * 4));
+  c->dev_ready = true;
+  return BFHE_OK;
+}
+
+// enqueue every level on the stream (directly, or under stream capture)
+static int enqueue_levels(bfhe_circuit *c) {
+  bfhe_ctx *x = c->ctx;
+  const size_t st = x->p.ct_stride;
+  for (uint32_t L = 0; L < c->levels.size(); L++) {
+    const uint32_t n = c->my_count[L];
+    if (n) {
+      int rc = launch_blind_rotate(x->P, x->p.method == BFHE_AP, c->d_desc + c->desc_off[L], (int)n, x->d_bk, x->d_twl, x->d_psiM,
+                                   c->d_ext, nullptr, x->force_g, x->stream, nullptr);
+      if (rc) return cuda_fail((cudaError_t)rc, "blind_rotate launch");
+      rc = launch_keyswitch(x->P, c->d_ext, c->d_desc + c->desc_off[L], (int)n, x->d_ksk, x->ksk_elem_bytes, x->stream);
+      if (rc) return cuda_fail((cudaError_t)rc, "keyswitch launch");
+    }
+    if (c->world > 1 && c->level_rpr[L]) {
+      u32 *base = c->slab + (size_t)c->levels[L].first_row * st;
+      const size_t cnt = (size_t)c->level_rpr[L] * st;
+      int nrc = g_nccl.AllGather(base + (size_t)c->rank * cnt, base, cnt, NCCL_UINT32, c->comm, x->stream);
+      if (nrc) { set_error(std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?")); return BFHE_ERR_NCCL; }
+    }
+    const size_t nn = c->not_off[L + 1] - c->not_off[L];
+    if (nn) {
+      int rc = launch_eval_not(x->P, c->d_not_in + c->not_off[L], c->d_not_out + c->not_off[L], (int)nn, x->stream);
+      if (rc) return cuda_fail((cudaError_t)rc, "eval_not launch");
+    }
+  }
+  return BFHE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plaintext evaluation (the reference's plaintext_flag path of Gate::Evaluate, src/gate.cpp:86-190)
+// ---------------------------------------------------------------------------------------------
+static void eval_plain(bfhe_circuit *c) {
+  const Netlist &nl = c->nl;
+  c->plain_wire.assign(nl.n_wires, 0);
+  std::vector<uint32_t> bus_base(nl.in_bits.size() + 1, 0);
+  for (size_t b = 0; b < nl.in_bits.size(); b++) bus_base[b + 1] = bus_base[b] + nl.in_bits[b];
+  for (uint32_t gi : c->topo) {
+    const NetGate &g = nl.gates[gi];
+    auto &w = c->plain_wire;
+    switch (g.kind) {
+    case GateKind::INPUT: w[g.out] = c->in_bits_set[bus_base[g.in0] + g.in1] & 1; break;
+    case GateKind::NOT: w[g.out] = !w[g.in0]; break;
+    case GateKind::AND: w[g.out] = w[g.in0] && w[g.in1]; break;
+    case GateKind::OR: w[g.out] = w[g.in0] || w[g.in1]; break;
+    case GateKind::XOR: w[g.out] = w[g.in0] ^ w[g.in1]; break;
+    case GateKind::OUTPUT: break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" bfhe_circuit *bfhe_circuit_create(bfhe_ctx *ctx) {
+  if (!ctx) { set_error("null context"); return nullptr; }
+  bfhe_circuit *c = new bfhe_circuit();
+  c->ctx = ctx;
+  return c;
+}
+extern "C" void bfhe_circuit_destroy(bfhe_circuit *c) {
+  if (!c) return;
+  free_device(c);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  delete c;
+}
+static int after_load(bfhe_circuit *c, const std::string &err) {
+  if (!err.empty()) { set_error(err); c->loaded = false; return BFHE_ERR_FORMAT; }
+  c->loaded = true;
+  c->planned = false;
+  c->has_input = false;
+  free_device(c);
+  return build_plan(c);
+}
+extern "C" int bfhe_circuit_read_file(bfhe_circuit *c, const char *path) {
+  if (!c || !path) return BFHE_ERR_ARG;
+  return after_load(c, parse_out_file(path, c->nl));
+}
+extern "C" int bfhe_circuit_read_bristol(bfhe_circuit *c, const char *path, int new_format) {
+  if (!c || !path) return BFHE_ERR_ARG;
+  return after_load(c, parse_bristol_file(path, new_format != 0, c->nl));
+}
+/* netlist straight from arrays: kind[i] in GateEnum order {INPUT, OUTPUT, NOT, AND, OR, XOR} (src/gate.h:51);
+ * INPUT: in0 = bus, in1 = bit, out = wire; OUTPUT: in0 = wire, out = output bit; others: wires */
+extern "C" int bfhe_circuit_load_netlist(bfhe_circuit *c, const uint8_t *kind, const uint32_t *in0, const uint32_t *in1,
+                                         const uint32_t *out, size_t count, uint32_t n_wires, const uint32_t *in_bits,
+                                         uint32_t n_in_buses, uint32_t out_bits) {
+  if (!c || !kind || !in0 || !in1 || !out || !in_bits) return BFHE_ERR_ARG;
+  Netlist nl;
+  nl.n_wires = n_wires;
+  nl.in_bits.assign(in_bits, in_bits + n_in_buses);
+  nl.out_bits = out_bits;
+  nl.gates.resize(count);
+  for (size_t i = 0; i < count; i++) {
+    if (kind[i] > (uint8_t)GateKind::XOR) return after_load(c, "unknown gate kind");
+    NetGate &g = nl.gates[i];
+    g.kind = (GateKind)kind[i]; g.in0 = in0[i]; g.in1 = in1[i]; g.out = out[i];
+    switch (g.kind) {
+    case GateKind::INPUT: nl.n_input++; break;
+    case GateKind::OUTPUT: nl.n_output++; break;
+    case GateKind::NOT: nl.n_not++; break;
+    case GateKind::AND: nl.n_and++; break;
+    case GateKind::OR: nl.n_or++; break;
+    case GateKind::XOR: nl.n_xor++; break;
+    }
+  }
+  c->nl = std::move(nl);
+  return after_load(c, "");
+}
+extern "C" int bfhe_circuit_get_netlist(const bfhe_circuit *c, uint8_t *kind, uint32_t *in0, uint32_t *in1, uint32_t *out, size_t cap,
+                                        uint32_t *count, uint32_t *n_wires) {
+  if (!c || !c->loaded) return BFHE_ERR_STATE;
+  if (count) *count = (uint32_t)c->nl.gates.size();
+  if (n_wires) *n_wires = c->nl.n_wires;
+  if (kind) {
+    if (cap < c->nl.gates.size()) return BFHE_ERR_ARG;
+    for (size_t i = 0; i < c->nl.gates.size(); i++) {
+      kind[i] = (uint8_t)c->nl.gates[i].kind; in0[i] = c->nl.gates[i].in0; in1[i] = c->nl.gates[i].in1; out[i] = c->nl.gates[i].out;
+    }
+  }
+  return BFHE_OK;
+}
+/* emit the reference's ".out" assembler text (what assemble_bristol writes, src/assemble.cpp:111-114,155-184,310-368,409-425) */
+extern "C" int bfhe_circuit_write_out(const bfhe_circuit *c, const char *path) {
+  if (!c || !c->loaded || !path) return BFHE_ERR_STATE;
+  FILE *f = std::fopen(path, "w");
+  if (!f) { set_error(std::string("cannot open ") + path); return BFHE_ERR_IO; }
+  const Netlist &nl = c->nl;
+  std::fprintf(f, "# Max depth 0\n");
+  for (size_t b = 0; b < 2; b++) std::fprintf(f, "# number input%zu bits %u\n", b + 1, b < nl.in_bits.size() ? nl.in_bits[b] : 0);
+  std::fprintf(f, "# number output1 bits %u\n", nl.out_bits);
+  for (const NetGate &g : nl.gates) {
+    switch (g.kind) {
+    case GateKind::INPUT: std::fprintf(f, "R%u = LOAD(In%u,%u)\n", g.out, g.in0 + 1, g.in1); break;
+    case GateKind::OUTPUT: std::fprintf(f, "Out%u = STORE(R%u) ! depth = 0\n", g.out, g.in0); break;
+    case GateKind::NOT: std::fprintf(f, "R%u = NOT(R%u) !depth = 0\n", g.out, g.in0); break;
+    case GateKind::AND: std::fprintf(f, "R%u = AND(R%u, R%u) !depth = 0\n", g.out, g.in0, g.in1); break;
+    case GateKind::OR: std::fprintf(f, "R%u = OR(R%u, R%u) !depth = 0\n", g.out, g.in0, g.in1); break;
+    case GateKind::XOR: std::fprintf(f, "R%u = XOR(R%u, R%u) !depth = 0\n", g.out, g.in0, g.in1); break;
+    }
+  }
+  std::fprintf(f, "# Assembler statistics\n# max depth supported: 0\n# max depth required: 0\n# max tower jump: 0\n# %u registers used\n", nl.n_wires);
+  std::fclose(f);
+  return BFHE_OK;
+}
+
+extern "C" int bfhe_circuit_set_flags(bfhe_circuit *c, int plaintext, int encrypted, int verify) {
+  if (!c) return BFHE_ERR_ARG;
+  const bool v = verify != 0;
+  // setVerify(true) forces both other modes on (src/circuit.cpp:833-840)
+  c->plaintext = plaintext != 0 || v;
+  c->encrypted = encrypted != 0 || v;
+  if (v != c->verify) { // verify mode materialises every NOT output: re-plan
+    c->verify = v;
+    if (c->loaded) {
+      free_device(c);
+      return build_plan(c);
+    }
+  }
+  return BFHE_OK;
+}
+extern "C" int bfhe_circuit_info(const bfhe_circuit *c, uint32_t *n_inputs, uint32_t *input_bits, uint32_t *n_output_bits,
+                                 uint32_t *n_gates, uint32_t *n_bootstraps, uint32_t *n_levels, uint32_t *max_width) {
+  if (!c || !c->loaded) return BFHE_ERR_STATE;
+  if (n_inputs) *n_inputs = (uint32_t)c->nl.in_bits.size();
+  if (input_bits)
+    for (size_t i = 0; i < 8; i++) input_bits[i] = i < c->nl.in_bits.size() ? c->nl.in_bits[i] : 0;
+  if (n_output_bits) *n_output_bits = c->nl.out_bits;
+  if (n_gates) *n_gates = c->nl.n_and + c->nl.n_or + c->nl.n_xor + c->nl.n_not;
+  if (n_bootstraps) *n_bootstraps = c->n_bootstraps;
+  if (n_levels) *n_levels = (uint32_t)c->levels.size() - 1;
+  if (max_width) *max_width = c->max_width;
+  return BFHE_OK;
+}
+extern "C" int bfhe_circuit_dump_gate_count(const bfhe_circuit *c, uint32_t *in, uint32_t *out, uint32_t *and_, uint32_t *or_,
+                                            uint32_t *xor_, uint32_t *not_) {
+  if (!c || !c->loaded) return BFHE_ERR_STATE;
+  if (in) *in = c->nl.n_input;
+  if (out) *out = c->nl.n_output;
+  if (and_) *and_ = c->nl.n_and;
+  if (or_) *or_ = c->nl.n_or;
+  if (xor_) *xor_ = c->nl.n_xor;
+  if (not_) *not_ = c->nl.n_not;
+  return BFHE_OK;
+}
+extern "C" int bfhe_get_nccl_unique_id(void *out128) {
+  if (!out128) return BFHE_ERR_ARG;
+  if (!load_nccl()) return BFHE_ERR_NCCL;
+  int rc = g_nccl.GetUniqueId(out128);
+  if (rc) { set_error("ncclGetUniqueId failed"); return BFHE_ERR_NCCL; }
+  return BFHE_OK;
+}
+extern "C" int bfhe_circuit_set_sharding(bfhe_circuit *c, int rank, int world, const void *id) {
+  if (!c || world < 1 || rank < 0 || rank >= world) return BFHE_ERR_ARG;
+  if (c->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+  c->rank = rank;
+  c->world = world;
+  if (world > 1 && id) { // id == NULL: plan only (tests of the partition on CPU)
+    if (c->ctx->device < 0) { set_error("sharded evaluation needs a CUDA device"); return BFHE_ERR_CUDA; }
+    if (!load_nccl()) return BFHE_ERR_NCCL;
+    BFHE_CUDA(cudaSetDevice(c->ctx->device));
+    Id128 uid;
+    std::memcpy(uid.b, id, 128);
+    int rc = g_nccl.CommInitRank(&c->comm, world, uid, rank);
+    if (rc) { set_error(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); return BFHE_ERR_NCCL; }
+  }
+  if (c->loaded) {
+    free_device(c);
+    return build_plan(c);
+  }
+  return BFHE_OK;
+}
+extern "C" int bfhe_circuit_level_plan(const bfhe_circuit *c, uint32_t level, int rank, int world, bfhe_gate *out, size_t cap,
+                                       uint32_t *count, uint32_t *first_row, uint32_t *rows_per_rank) {
+  if (!c || !c->planned || level >= c->levels.size()) return BFHE_ERR_ARG;
+  if (world != c->world) { set_error("plan was built for a different world size"); return BFHE_ERR_STATE; }
+  uint32_t b, n;
+  my_slice(c, level, rank, &b, &n);
+  if (count) *count = n;
+  if (first_row) *first_row = c->levels[level].first_row;
+  if (rows_per_rank) *rows_per_rank = c->level_rpr[level];
+  if (out) {
+    if (cap < n) return BFHE_ERR_ARG;
+    std::memcpy(out, c->levels[level].gates.data() + b, n * sizeof(bfhe_gate));
+  }
+  return BFHE_OK;
+}
+extern "C" int bfhe_circuit_plan_misc(const bfhe_circuit *c, uint32_t *total_rows, uint32_t *fresh_base, uint32_t *n_levels_incl_input,
+                                      uint32_t *out_rows /*[out_bits]*/, uint32_t *not_count, uint32_t level,
+                                      uint32_t *not_pairs /*[2*not_count] in,out*/) {
+  if (!c || !c->planned) return BFHE_ERR_STATE;
+  if (total_rows) *total_rows = c->total_rows;
+  if (fresh_base) *fresh_base = c->fresh_base;
+  if (n_levels_incl_input) *n_levels_incl_input = (uint32_t)c->levels.size();
+  if (out_rows)
+    for (uint32_t b = 0; b < c->nl.out_bits; b++) out_rows[b] = c->wire_row[c->out_wire[b]] | (c->wire_neg[c->out_wire[b]] ? 0x80000000u : 0);
+  if (level < c->levels.size()) {
+    if (not_count) *not_count = (uint32_t)c->levels[level].nots.size();
+    if (not_pairs)
+      for (size_t k = 0; k < c->levels[level].nots.size(); k++) {
+        not_pairs[2 * k] = c->levels[level].nots[k].in_row;
+        not_pairs[2 * k + 1] = c->levels[level].nots[k].out_row;
+      }
+  }
+  return BFHE_OK;
+}
+
+extern "C" int bfhe_circuit_reset(bfhe_circuit *c) {
+  if (!c || !c->loaded) return BFHE_ERR_STATE;
+  // Circuit::Reset clears the mode flags as well (src/circuit.cpp:378-381); callers set them again afterwards,
+  // exactly as the reference harnesses do (src/test_adder.cpp:228-233)
+  c->has_input = false;
+  c->done = false;
+  c->device_ms = c->host_ms = 0;
+  c->verify_mismatches = c->verify_checked = 0;
+  return BFHE_OK;
+}
+
+extern "C" int bfhe_circuit_set_input(bfhe_circuit *c, const uint8_t *bits, size_t nbits, uint64_t seed) {
+  if (!c || !c->planned || !bits) return BFHE_ERR_STATE;
+  if (nbits != c->n_in) { set_error("SetInput: expected " + std::to_string(c->n_in) + " bits, got " + std::to_string(nbits)); return BFHE_ERR_ARG; }
+  c->in_bits_set.assign(bits, bits + nbits);
+  c->has_input = true;
+  c->done = false;
+  if (c->encrypted) {
+    if (!c->dev_ready) {
+      int rc = upload_plan(c);
+      if (rc) return rc;
+    }
+    bfhe_ctx *x = c->ctx;
+    const size_t st = x->p.ct_stride;
+    // fresh encryptions on the host (deterministic in the seed, so every rank holds the same rows); the
+    // Bootstrap that Encrypt's BOOTSTRAPPED default applies (src/circuit.cpp:506) is level 0 of the plan
+    std::vector<u32> fresh((size_t)c->n_in * st);
+    int rc = bfhe_encrypt(x, bits, nbits, seed, fresh.data());
+    if (rc) return rc;
+    BFHE_CUDA(cudaMemcpyAsync(c->slab + (size_t)c->fresh_base * st, fresh.data(), fresh.size() * 4, cudaMemcpyHostToDevice, x->stream));
+    BFHE_CUDA(cudaStreamSynchronize(x->stream));
+  }
+  return BFHE_OK;
+}
+
+extern "C" int bfhe_circuit_clock(bfhe_circuit *c, uint8_t *out_bits, size_t cap, uint8_t *plain_out_bits) {
+  if (!c || !c->planned) return BFHE_ERR_STATE;
+  if (!c->has_input) { set_error("Clock before SetInput"); return BFHE_ERR_STATE; }
+  if (c->done) { set_error("done ckt clocked! should reset"); return BFHE_ERR_STATE; } // src/circuit.cpp:538-541
+  const uint32_t nout = c->nl.out_bits;
+  if (cap < nout) return BFHE_ERR_ARG;
+  auto t0 = std::chrono::steady_clock::now();
+  if (c->plaintext || c->verify) {
+    eval_plain(c);
+    uint8_t *dst = plain_out_bits ? plain_out_bits : (c->encrypted ? nullptr : out_bits);
+    if (dst)
+      for (uint32_t b = 0; b < nout; b++) dst[b] = c->plain_wire[c->out_wire[b]];
+  }
+  if (c->encrypted) {
+    bfhe_ctx *x = c->ctx;
+    std::lock_guard<std::mutex> lk(x->mtx);
+    BFHE_CUDA(cudaSetDevice(x->device));
+    const size_t st = x->p.ct_stride;
+    cudaEvent_t e0, e1;
+    BFHE_CUDA(cudaEventCreate(&e0));
+    BFHE_CUDA(cudaEventCreate(&e1));
+    BFHE_CUDA(cudaEventRecord(e0, x->stream));
+    int rc = BFHE_OK;
+    if (c->use_graph && c->world == 1) {
+      if (!c->graph) {
+        cudaGraph_t g = nullptr;
+        BFHE_CUDA(cudaStreamBeginCapture(x->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_levels(c);
+        cudaError_t ce = cudaStreamEndCapture(x->stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+        ce = cudaGraphInstantiate(&c->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+      }
+      BFHE_CUDA(cudaGraphLaunch(c->graph, x->stream));
+    } else {
+      rc = enqueue_levels(c);
+      if (rc) return rc;
+    }
+    BFHE_CUDA(cudaEventRecord(e1, x->stream));
+    BFHE_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->device_ms += ms;
+    // OUTPUT gates: decrypt on the host (src/circuit.cpp:796-801)
+    std::vector<u32> rows;
+    if (c->verify) {
+      rows.resize((size_t)c->total_rows * st);
+      BFHE_CUDA(cudaMemcpy(rows.data(), c->slab, rows.size() * 4, cudaMemcpyDeviceToHost));
+      std::vector<uint8_t> dec(c->total_rows);
+      rc = bfhe_decrypt(x, rows.data(), c->total_rows, dec.data());
+      if (rc) return rc;
+      // gate-by-gate check of every wire that owns a ciphertext against the plaintext evaluation
+      // (src/gate.cpp:113-120,153-160,174-181,206-213 -- reported, not "fixed")
+      for (uint32_t w = 0; w < c->nl.n_wires; w++) {
+        if (c->wire_row[w] == 0xffffffffu) continue;
+        const uint8_t v = dec[c->wire_row[w]] ^ c->wire_neg[w];
+        c->verify_checked++;
+        if (v != c->plain_wire[w]) c->verify_mismatches++;
+      }
+      for (uint32_t b = 0; b < nout; b++) out_bits[b] = dec[c->wire_row[c->out_wire[b]]] ^ c->wire_neg[c->out_wire[b]];
+    } else {
+      std::vector<u32> orow((size_t)nout * st);
+      for (uint32_t b = 0; b < nout; b++)
+        BFHE_CUDA(cudaMemcpyAsync(orow.data() + (size_t)b * st, c->slab + (size_t)c->wire_row[c->out_wire[b]] * st, st * 4,
+                                  cudaMemcpyDeviceToHost, x->stream));
+      BFHE_CUDA(cudaStreamSynchronize(x->stream));
+      std::vector<uint8_t> dec(nout);
+      rc = bfhe_decrypt(x, orow.data(), nout, dec.data());
+      if (rc) return rc;
+      for (uint32_t b = 0; b < nout; b++) out_bits[b] = dec[b] ^ c->wire_neg[c->out_wire[b]];
+    }
+  }
+  c->done = true;
+  c->host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return BFHE_OK;
+}
+
+extern "C" int bfhe_circuit_stats(const bfhe_circuit *c, double *device_ms, double *host_ms, uint64_t *verify_mismatches) {
+  if (!c) return BFHE_ERR_ARG;
+  if (device_ms) *device_ms = c->device_ms;
+  if (host_ms) *host_ms = c->host_ms;
+  if (verify_mismatches) *verify_mismatches = c->verify_mismatches;
+  return BFHE_OK;
+}
+extern "C" int bfhe_circuit_use_graph(bfhe_circuit *c, int on) {
+  if (!c) return BFHE_ERR_ARG;
+  c->use_graph = on != 0;
+  return BFHE_OK;
+}
+/* wire-level ciphertext access for parity tests: row of output bit b (host copy) */
+extern "C" int bfhe_circuit_download_slab(bfhe_circuit *c, uint32_t *host, size_t rows_cap) {
+  if (!c || !c->dev_ready) return BFHE_ERR_STATE;
+  if (rows_cap < c->total_rows) return BFHE_ERR_ARG;
+  BFHE_CUDA(cudaSetDevice(c->ctx->device));
+  BFHE_CUDA(cudaMemcpy(host, c->slab, (size_t)c->total_rows * c->ctx->p.ct_stride * 4, cudaMemcpyDeviceToHost));
+  return BFHE_OK;
+}
