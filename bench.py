@@ -197,7 +197,8 @@ def main():
     ctx = B.Context(B.STD128_OPT, B.GINX, local)
     ctx.keygen(1)   # keys from seed 1 (config 3), replicated on every GPU
     ctx.btkeygen(2)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # every kernel of the engine is launched on this stream; the events below sit on it too
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     count = args.gates
@@ -266,7 +267,8 @@ def main():
                 "peak": imad_peak / 1e12, "unit": "TIMAD/s", "frac": achieved_imad / imad_peak,
                 "peak_source": "measured live: register-only IMAD microbenchmark (bfhe_microbench_int), 148 SMs",
                 "work_per_unit": "%d IMAD-class instr per bootstrapped gate (3 x 45.25M modular multiplications, SURVEY 8(d))" % W_IMAD,
-                "kernel_ms_per_launch": 1e3 * br_s_per_launch, "kernel_share_of_step": br_ms / (dev_ms if world == 1 else br_ms + ks_ms + nt_ms),
+                "kernel_ms_per_launch": 1e3 * br_s_per_launch, "kernel_share_of_step": br_ms / (br_ms + ks_ms + nt_ms),
+                "step_ms_by_kernel": {"blind_rotate": br_ms / args.steps, "keyswitch": ks_ms / args.steps, "eval_not": nt_ms / args.steps},
                 "traffic": None,
                 "hbm": {"achieved": boots_per_launch * hbm_bytes_per_boot / br_s_per_launch / 1e9, "peak": peak_hbm(),
                         "unit": "GB/s", "bytes_per_unit": hbm_bytes_per_boot,

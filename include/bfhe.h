@@ -57,8 +57,9 @@ bfhe_ctx *bfhe_create(int paramset, int method, int device /* CUDA ordinal, -1 =
 void bfhe_destroy(bfhe_ctx *);
 int bfhe_get_params(const bfhe_ctx *, bfhe_params *out);
 const char *bfhe_last_error(void);
-/* launch stream for every subsequent kernel (a cudaStream_t, e.g. torch's current stream); NULL = own stream */
-int bfhe_set_stream(bfhe_ctx *, void *cuda_stream);
+/* launch stream for every subsequent kernel: a cudaStream_t (e.g. torch's current stream; NULL = the legacy default
+ * stream), or use_own != 0 to go back to the context's private non-blocking stream (the initial state) */
+int bfhe_set_stream(bfhe_ctx *, void *cuda_stream, int use_own);
 int bfhe_sync(bfhe_ctx *);
 
 /* ---- keys: KeyGen() / BTKeyGen(sk)  (src/circuit.cpp:90-91) ---- */

@@ -70,7 +70,7 @@ def lib():
     L.bfhe_destroy.restype = None
     L.bfhe_get_params.argtypes = [vp, C.POINTER(Params)]
     L.bfhe_last_error.restype = C.c_char_p
-    L.bfhe_set_stream.argtypes = [vp, vp]
+    L.bfhe_set_stream.argtypes = [vp, vp, C.c_int]
     L.bfhe_sync.argtypes = [vp]
     L.bfhe_keygen.argtypes = [vp, C.c_uint64]
     L.bfhe_btkeygen.argtypes = [vp, C.c_uint64]
@@ -219,8 +219,9 @@ class Context:
         return out
 
     # device
-    def set_stream(self, cuda_stream_handle):
-        self._ck(self.L.bfhe_set_stream(self.h, cuda_stream_handle))
+    def set_stream(self, cuda_stream_handle, use_own=False):
+        """cuda_stream_handle: integer cudaStream_t (0 / None = legacy default stream); use_own: private stream"""
+        self._ck(self.L.bfhe_set_stream(self.h, cuda_stream_handle or None, int(use_own)))
 
     def sync(self):
         self._ck(self.L.bfhe_sync(self.h))

@@ -171,9 +171,9 @@ extern "C" int bfhe_get_params(const bfhe_ctx *c, bfhe_params *out) {
   *out = c->p;
   return BFHE_OK;
 }
-extern "C" int bfhe_set_stream(bfhe_ctx *c, void *s) {
+extern "C" int bfhe_set_stream(bfhe_ctx *c, void *s, int use_own) {
   if (!c || c->device < 0) return BFHE_ERR_STATE;
-  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  c->stream = use_own ? c->own_stream : (cudaStream_t)s; // s == NULL is the legacy default stream, as everywhere in CUDA
   return BFHE_OK;
 }
 extern "C" int bfhe_sync(bfhe_ctx *c) {
