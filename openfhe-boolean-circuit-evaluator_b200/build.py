@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 LIB = os.path.join(HERE, "libbfhe_b200.so")
+TB = os.path.join(HERE, "examples", "tb_circuit")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CCBIN = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
@@ -42,6 +43,10 @@ def build(force=False, verbose=False):
             subprocess.check_call(cmd)
         objs.append(o)
     subprocess.check_call([NVCC, "-ccbin", CCBIN, "-shared", "-o", LIB] + objs + ["-lgomp", "-ldl", "-cudart", "static"])
+    # C++ example written against the reference-shaped headers (host/circuit.h, host/binfhecontext.h)
+    ex = os.path.join(HERE, "examples", "tb_circuit.cpp")
+    if os.path.exists(ex):
+        subprocess.check_call([CCBIN, "-O2", "-std=c++17", "-o", TB, ex, "-L" + HERE, "-lbfhe_b200", "-Wl,-rpath," + HERE])
     return LIB
 
 

@@ -101,3 +101,20 @@ def test_out_file_path_on_gpu(bfhe, tmp_path):
     c.ReadFile(p)
     for t, v in enumerate(VECTORS["adder_2bit"]["vectors"][:5]):
         assert _run_encrypted(c, v, seed=t) == v["golden"]
+
+
+def test_cpp_host_mirror_tb_adder(bfhe, tmp_path):
+    """The C++ host layer (host/circuit.h + host/binfhecontext.h, the reference's class / method names) drives the same
+    engine: examples/tb_circuit.cpp is TB_adder_2bit rewritten against it; exit code 0 = plaintext, encrypted+verify and
+    the single-gate EvalBinGate / EvalNOT / throw-on-alias behaviour all pass."""
+    import os
+    import subprocess
+    ctx = shared_keys(bfhe, bfhe.TOY, bfhe.GINX, 0)
+    c0 = load_circuit(bfhe, ctx, "adder_2bit")
+    p = tmp_path / "adder_2bit.out"
+    c0.write_out(p)
+    exe = os.path.join(os.path.dirname(bfhe.LIB_PATH), "examples", "tb_circuit")
+    assert os.path.exists(exe), "run build() first"
+    r = subprocess.run([exe, str(p), "-s", "STD128_OPT", "-m", "GINX", "-n", "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ALL PASSED" in r.stdout
