@@ -234,7 +234,7 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
                     u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
   using Cfg = BrCfg<LOGN, DG, LOGBG, G, AP>;
   constexpr int N = Cfg::N, E = Cfg::E, C = Cfg::C, ROWS = Cfg::ROWS, W = Cfg::W, NPAD = Cfg::NPAD;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   u32 *dct = reinterpret_cast<u32 *>(smem_raw);                 // [G][ROWS][N]
   u32 *s_tw = dct + Cfg::dct_words;                             // fw | fws | iw | iws
   u32 *s_psiM = s_tw + 4 * N;                                   // [2N] Montgomery psi^k (GINX)
@@ -451,6 +451,288 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// blind rotation, latency variant: ONE gate per CTA, one warp per decomposition row (2*DG warps), so the 2*DG
+// forward NTTs of a step run concurrently and the step's critical path is INTT -> NTT -> MAC instead of
+// INTT -> DG x NTT -> MAC.  Used for narrow wavefronts (deep circuits: AES, SHA-256), where there are fewer gates
+// than the GPU has room for and latency per level is what matters.
+// The step's bootstrapping-key tile (GINX: 2 RGSW = 128 KB) is prefetched into shared memory by a TMA bulk copy
+// (cp.async.bulk + mbarrier complete_tx) issued right after the previous step's external product, so the
+// L2 latency of the key is hidden behind the next step's transforms at no register or issue cost.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(
+                   smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+
+template <int LOGN, int DG, int LOGBG, bool AP> struct LatCfg {
+  static constexpr int N = 1 << LOGN, E = N / 32, C = E / 4, ROWS = 2 * DG;
+  static constexpr int W = ROWS, THREADS = 32 * W;
+  static constexpr int NPAD = 1024;
+  static constexpr int KEYPOLYS = AP ? ROWS * 2 : 2 * ROWS * 2;
+  // words: dct | digits | key tile | twiddles | psi powers ; then u16 idx + u16 active list ; then the mbarrier
+  static constexpr size_t words = (size_t)ROWS * N + 2 * N + (size_t)KEYPOLYS * N + 4 * N + (AP ? 0 : 2 * N);
+  static constexpr size_t smem_bytes = words * 4 + 2 * NPAD * 2 + 16;
+};
+
+template <int LOGN, int DG, int LOGBG, bool AP>
+__global__ void __launch_bounds__(64 * DG, 1)
+blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count,
+                        const u32 *__restrict__ bk, const u32 *__restrict__ g_twl, const u32 *__restrict__ g_psiM,
+                        u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
+  using Cfg = LatCfg<LOGN, DG, LOGBG, AP>;
+  constexpr int N = Cfg::N, E = Cfg::E, C = Cfg::C, ROWS = Cfg::ROWS, W = Cfg::W, NPAD = Cfg::NPAD, KEYPOLYS = Cfg::KEYPOLYS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u32 *dct = reinterpret_cast<u32 *>(smem_raw);         // [ROWS][N]
+  u32 *dig = dct + (size_t)ROWS * N;                    // [2][N] packed signed digits of the accumulator
+  u32 *s_key = dig + 2 * N;                             // [KEYPOLYS][N] this step's key tile
+  u32 *s_tw = s_key + (size_t)KEYPOLYS * N;             // fw | fws | iw | iws
+  u32 *s_psiM = s_tw + 4 * N;                           // [2N] (GINX)
+  u16 *s_idx = reinterpret_cast<u16 *>(s_psiM + (AP ? 0 : 2 * N)); // [NPAD] monomial exponent / AP digit per step
+  u16 *s_list = s_idx + NPAD;                           // [NPAD] steps that do work
+  u64 *s_bar = reinterpret_cast<u64 *>(s_list + NPAD);
+  __shared__ u32 s_b, s_nact;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = warp & 1, l = warp >> 1; // this warp transforms digit l of accumulator component c (row c + 2l)
+  const size_t gi = blockIdx.x;
+  const u32 Q = P.Q, q = P.q, n = P.n;
+  const DevGate dg = gates[gi];
+
+  for (int i = tid; i < 4 * N; i += Cfg::THREADS) s_tw[i] = g_twl[i];
+  if (!AP)
+    for (int i = tid; i < 2 * N; i += Cfg::THREADS) s_psiM[i] = g_psiM[i];
+  const TwTabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  { // LWE prep (same as the throughput kernel)
+    const u32 gate = dg.op & 0xff;
+    for (u32 i = tid; i <= n; i += Cfg::THREADS) {
+      u32 x = dg.in0[i];
+      if (dg.op & OP_NEG0) x = (i == n) ? (q / 4 + q - x) % q : (q - x) % q;
+      u32 v;
+      if (gate == OP_BOOTSTRAP) v = (i == n) ? (x + q / 4) % q : x;
+      else {
+        u32 y = dg.in1[i];
+        if (dg.op & OP_NEG1) y = (i == n) ? (q / 4 + q - y) % q : (q - y) % q;
+        v = (gate == OP_XOR_FAST || gate == OP_XNOR_FAST) ? (2 * (x + q - y)) % q : (x + y) % q;
+      }
+      if (i == n) s_b = v;
+      else {
+        const u32 aneg = (q - v) % q;
+        if (!AP) s_idx[i] = (u16)(aneg * P.factor);
+        else {
+          u32 a = aneg;
+          for (u32 k = 0; k < P.dR; k++, a /= P.baseR) s_idx[i * P.dR + k] = (u16)(a % P.baseR);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int nsteps = AP ? n * P.dR : n;
+  if (tid == 0) { // steps that do work (AP skips zero digits; X^0 - 1 = 0 makes a zero GINX exponent a no-op as well)
+    u32 na = 0;
+    for (int s = 0; s < nsteps; s++)
+      if (s_idx[s] != 0) s_list[na++] = (u16)s;
+    s_nact = na;
+  }
+  __syncthreads();
+  const int nact = s_nact;
+  constexpr u32 KEYBYTES = (u32)KEYPOLYS * N * 4;
+  auto key_src = [&](int step) -> const u32 * {
+    if (!AP) return bk + (size_t)step * KEYPOLYS * N;
+    const u32 a0 = s_idx[step], i = step / P.dR, k = step % P.dR;
+    return bk + (((size_t)i * (P.baseR - 1) + (a0 - 1)) * P.dR + k) * (size_t)KEYPOLYS * N;
+  };
+  if (tid == 0 && nact > 0) {
+    mbar_expect_tx(s_bar, KEYBYTES);
+    const u32 *src = key_src(s_list[0]);
+#pragma unroll 1
+    for (u32 off = 0; off < KEYBYTES; off += 16384) bulk_g2s(reinterpret_cast<char *>(s_key) + off, reinterpret_cast<const char *>(src) + off, min(16384u, KEYBYTES - off), s_bar);
+  }
+
+  // accumulator (coefficient form) lives in the registers of warps 0 and 1
+  u32 acc[E];
+#pragma unroll
+  for (int k = 0; k < E; k++) acc[k] = 0;
+  if (warp == 1) {
+    const u32 gate = dg.op & 0xff;
+    const u32 q1 = P.gate_const[gate == OP_BOOTSTRAP ? OP_AND : gate], q2 = (q1 + q / 2) % q;
+    const u32 b = s_b, Q8 = P.Q8, Q8n = Q - P.Q8;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const u32 idx = lane + 32 * k;
+      if (idx % P.factor == 0) {
+        const u32 t = (b + q - idx / P.factor) % q;
+        const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
+        acc[k] = in ? Q8n : Q8;
+      }
+    }
+  }
+  const u32 eA = 2 * brev(lane, 5) + 1;
+  constexpr u32 FIELD = LOGBG; // packed digit field width: DG * LOGBG <= 32
+
+  for (int j = 0; j < nact; j++) {
+    const int step = s_list[j];
+    // ---- phase 1: warps 0,1 close the previous step (INTT, accumulate) and decompose ----
+    if (warp < 2) {
+      if (j > 0) {
+        u32 x[E];
+        u32 *rb = dct + (size_t)warp * N;
+        row_load<E>(rb, x, lane);
+        ntt_inverse<LOGN, AP ? 8 : 4>(x, rb, P, tt, lane);
+#pragma unroll
+        for (int k = 0; k < E; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
+      }
+#pragma unroll
+      for (int k = 0; k < E; k++) {
+        i32 d = (acc[k] < (Q >> 1)) ? (i32)acc[k] : (i32)acc[k] - (i32)Q;
+        u32 packed = 0;
+#pragma unroll
+        for (int ll = 0; ll < DG; ll++) {
+          const i32 r = (i32)((u32)d << (32 - LOGBG)) >> (32 - LOGBG);
+          d = (d - r) >> LOGBG;
+          packed |= ((u32)r & ((1u << FIELD) - 1)) << (FIELD * ll);
+        }
+        dig[warp * N + lane + 32 * k] = packed;
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: every warp transforms its own digit polynomial ----
+    {
+      u32 x[E];
+#pragma unroll
+      for (int k = 0; k < E; k++) {
+        const u32 pk = dig[c * N + lane + 32 * k];
+        const i32 r = (i32)(pk << (32 - FIELD * (l + 1))) >> (32 - FIELD);
+        x[k] = min((u32)r, (u32)r + Q);
+      }
+      u32 *buf = dct + (size_t)warp * N;
+      ntt_forward<LOGN>(x, buf, P, tt, lane);
+      row_store<E>(buf, x, lane);
+    }
+    __syncthreads();
+    // ---- phase 3: external product against the staged key tile ----
+    mbar_wait(s_bar, (u32)(j & 1));
+    for (int qc = warp; qc < C; qc += W) {
+      u32 fp[4], fn[4];
+      if (!AP) {
+        const u32 m = s_idx[step], mask = 2 * N - 1;
+        const u32 ia = (m * eA) & mask;
+        const u32 A = s_psiM[ia], Ai = s_psiM[(2 * N - ia) & mask];
+        const u32 om = Q - P.oneM;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const u32 eB = 2 * ((brev(r, 2) << (LOGN - 2)) | (brev(qc, LOGN - 7) << 5));
+          const u32 ib = (m * eB) & mask;
+          const u32 Bv = s_psiM[ib], Bi = s_psiM[(2 * N - ib) & mask];
+          fp[r] = redc((u64)A * Bv, Q, P.qinv_neg) + om;
+          fn[r] = redc((u64)Ai * Bi, Q, P.qinv_neg) + om;
+        }
+      }
+      u32 *gd = dct + Lay<E>::chunk_off(lane, qc);
+      const u32 *kb = s_key + (qc * 32 + lane) * 4;
+      uint4 dv[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) dv[r] = *reinterpret_cast<const uint4 *>(gd + (size_t)r * N);
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) {
+        u64 sp[4] = {0, 0, 0, 0}, sn[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+          const uint4 kp = *reinterpret_cast<const uint4 *>(kb + (size_t)(r * 2 + cc) * N);
+          sp[0] += (u64)dv[r].x * kp.x; sp[1] += (u64)dv[r].y * kp.y; sp[2] += (u64)dv[r].z * kp.z; sp[3] += (u64)dv[r].w * kp.w;
+          if (!AP) {
+            const uint4 kn = *reinterpret_cast<const uint4 *>(kb + (size_t)((ROWS + r) * 2 + cc) * N);
+            sn[0] += (u64)dv[r].x * kn.x; sn[1] += (u64)dv[r].y * kn.y; sn[2] += (u64)dv[r].z * kn.z; sn[3] += (u64)dv[r].w * kn.w;
+          }
+        }
+        u32 out[4];
+#pragma unroll
+        for (int sl = 0; sl < 4; sl++) {
+          const u32 pp = redc(sp[sl], Q, P.qinv_neg);
+          if (AP) out[sl] = pp;
+          else out[sl] = redc((u64)pp * fp[sl] + (u64)redc(sn[sl], Q, P.qinv_neg) * fn[sl], Q, P.qinv_neg);
+        }
+        *reinterpret_cast<uint4 *>(gd + (size_t)cc * N) = make_uint4(out[0], out[1], out[2], out[3]);
+      }
+    }
+    __syncthreads();
+    // ---- prefetch the next step's key tile while the next transforms run ----
+    if (tid == 0 && j + 1 < nact) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy reads above, async-proxy writes below
+      mbar_expect_tx(s_bar, KEYBYTES);
+      const u32 *src = key_src(s_list[j + 1]);
+#pragma unroll 1
+      for (u32 off = 0; off < KEYBYTES; off += 16384) bulk_g2s(reinterpret_cast<char *>(s_key) + off, reinterpret_cast<const char *>(src) + off, min(16384u, KEYBYTES - off), s_bar);
+    }
+  }
+
+  // ---- epilogue ----
+  if (warp < 2) {
+    if (nact > 0) {
+      u32 x[E];
+      u32 *rb = dct + (size_t)warp * N;
+      row_load<E>(rb, x, lane);
+      ntt_inverse<LOGN, AP ? 8 : 4>(x, rb, P, tt, lane);
+#pragma unroll
+      for (int k = 0; k < E; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
+    }
+    if (acc_dbg) {
+#pragma unroll
+      for (int k = 0; k < E; k++) acc_dbg[(gi * 2 + warp) * N + lane + 32 * k] = acc[k];
+    }
+    u32 *e = ext + gi * (N + 4);
+    const u64 qKS = P.qKS;
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < E; k++) {
+        const u32 jj = lane + 32 * k;
+        const u32 v = (jj == 0) ? acc[k] : (acc[k] == 0 ? 0 : Q - acc[k]);
+        const u32 pos = (jj == 0) ? 0 : N - jj;
+        e[pos] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+      }
+    } else if (lane == 0) {
+      const u32 v = csub(acc[0] + P.Q8, Q);
+      e[N] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+    }
+  }
+}
+
+template <int LOGN, int DG, int LOGBG, bool AP>
+static int launch_lat_inst(const DevConst &P, const DevGate *d_gates, int count, const u32 *d_bk, const u32 *d_twl,
+                           const u32 *d_psiM, u32 *d_ext, u32 *d_acc, cudaStream_t st, LaunchInfo *info) {
+  using Cfg = LatCfg<LOGN, DG, LOGBG, AP>;
+  auto kern = blind_rotate_lat_kernel<LOGN, DG, LOGBG, AP>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  if (count <= 0) return 0;
+  if (info) { info->gates_per_cta = 1; info->ctas = count; info->smem_bytes = Cfg::smem_bytes; }
+  kern<<<count, Cfg::THREADS, Cfg::smem_bytes, st>>>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc);
+  return (int)cudaGetLastError();
+}
+
 template <int LOGN, int DG, int LOGBG, int G, bool AP>
 static int launch_br_inst(const DevConst &P, const DevGate *d_gates, int count, const u32 *d_bk, const u32 *d_twl,
                           const u32 *d_psiM, u32 *d_ext, u32 *d_acc, cudaStream_t st, LaunchInfo *info) {
@@ -486,6 +768,8 @@ template <int LOGN, int DG, int LOGBG> static int br_attrs() {
     rc |= launch_br_g<LOGN, DG, LOGBG, false>(G, P, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
     rc |= launch_br_g<LOGN, DG, LOGBG, true>(G, P, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
   }
+  rc |= launch_lat_inst<LOGN, DG, LOGBG, false>(P, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+  rc |= launch_lat_inst<LOGN, DG, LOGBG, true>(P, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
   return rc;
 }
 static int keyswitch_attrs();
@@ -503,8 +787,19 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // gates per CTA: fill the SMs first (latency), then share key traffic (throughput)
-  int G = force_g > 0 ? force_g : (count <= sms ? 1 : (count <= 2 * sms ? 2 : 4));
+  // narrow wavefront (fewer than 4 gates per SM): the latency variant -- one gate per CTA, one warp per digit row;
+  // wide wavefront: the throughput variant -- G gates per CTA share every bootstrapping-key word
+  const bool lat = force_g == 8 || (force_g == 0 && count <= 4 * sms);
+  if (lat) {
+    if (P.N == 1024 && P.dG == 4 && P.logBG == 7)
+      return method_ap ? launch_lat_inst<10, 4, 7, true>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
+                       : launch_lat_inst<10, 4, 7, false>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);
+    if (P.N == 512 && P.dG == 3 && P.logBG == 9)
+      return method_ap ? launch_lat_inst<9, 3, 9, true>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
+                       : launch_lat_inst<9, 3, 9, false>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);
+    return (int)cudaErrorInvalidValue;
+  }
+  int G = force_g > 0 ? force_g : 4;
   if (P.N == 1024 && P.dG == 4 && P.logBG == 7) {
     return method_ap ? launch_br_g<10, 4, 7, true>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
                      : launch_br_g<10, 4, 7, false>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);

@@ -45,7 +45,8 @@ def _random_gates(bfhe, rng, n_in, count, ops):
 
 
 @pytest.mark.parametrize("ps_name,m_name", CONFIGS)
-def test_blind_rotate_accumulator(bfhe, orc, ps_name, m_name):
+@pytest.mark.parametrize("gpc", [4, 8])
+def test_blind_rotate_accumulator(bfhe, orc, ps_name, m_name, gpc):
     """a9-a12: accumulator after the whole blind rotation, coefficient form, vs the oracle's evaluation-form loop."""
     ctx, o = _setup(bfhe, orc, ps_name, m_name)
     rng = np.random.default_rng(3)
@@ -55,7 +56,11 @@ def test_blind_rotate_accumulator(bfhe, orc, ps_name, m_name):
     gates = _random_gates(bfhe, rng, 6, 5, ops)
     slab = ctx.slab(6 + 5)
     slab.upload(cts)
-    acc = ctx.dbg_blind_rotate(slab, gates)
+    ctx.dbg_set_gates_per_cta(gpc)
+    try:
+        acc = ctx.dbg_blind_rotate(slab, gates)
+    finally:
+        ctx.dbg_set_gates_per_cta(0)
     for i, g in enumerate(gates):
         prep = o.prep(int(g["op"]), cts[g["in0"]], cts[g["in1"]])
         ref = o.blind_rotate(int(g["op"]) & 0xff, prep)
@@ -64,7 +69,7 @@ def test_blind_rotate_accumulator(bfhe, orc, ps_name, m_name):
 
 
 @pytest.mark.parametrize("ps_name,m_name", CONFIGS)
-@pytest.mark.parametrize("gpc", [1, 2, 4])
+@pytest.mark.parametrize("gpc", [1, 2, 4, 8])  # 8 = latency variant (one gate per CTA, TMA-staged key)
 def test_bingate_bit_exact(bfhe, orc, ps_name, m_name, gpc):
     """a7: output LWE ciphertexts of a wavefront are bit-identical to the oracle for every gate type."""
     ctx, o = _setup(bfhe, orc, ps_name, m_name)

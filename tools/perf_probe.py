@@ -20,7 +20,7 @@ n_in = 4096
 bits = np.random.default_rng(0).integers(0, 2, n_in)
 cts = ctx.encrypt(bits, seed=1)
 res = []
-for gpc, count in ((1, 148), (2, 296), (4, 592), (4, 2368), (4, 9472), (2, 4736), (1, 2368)):
+for gpc, count in ((8, 1), (8, 100), (8, 148), (8, 200), (8, 296), (8, 592), (1, 148), (2, 296), (4, 592), (4, 2368), (4, 9472)):
     slab = ctx.slab(n_in + count)
     slab.upload(cts)
     g = np.zeros(count, dtype=B.GATE_DTYPE)
