@@ -62,5 +62,6 @@ int launch_dbg_ntt(const DevConst &P, const u32 *d_a, const u32 *d_b, u32 *d_rt,
                    void *stream);
 int launch_microbench(int which, u32 *d_sink, int iters, int *threads_total, int *ops_per_thread_iter, void *stream);
 int blind_rotate_set_attrs();
+bool kernels_built_for_solinas_q();
 
 } // namespace bfhe

@@ -69,6 +69,10 @@ extern "C" bfhe_ctx *bfhe_create(int paramset, int method, int device) {
     set_error("ring modulus outside (2^26, 2^27): the lazy-reduction ranges of the kernels assume 32Q < 2^32");
     return nullptr;
   }
+  if (kernels_built_for_solinas_q() && p.Q != (1ull << 27) - (1ull << 11) + 1) {
+    set_error("kernels are specialised for Q = 2^27 - 2^11 + 1; rebuild with -DBFHE_GENERIC_Q for another modulus");
+    return nullptr;
+  }
   bfhe_ctx *c = new bfhe_ctx();
   c->p = p;
   c->device = device;

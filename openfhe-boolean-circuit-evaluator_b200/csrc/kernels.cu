@@ -28,12 +28,39 @@ namespace bfhe {
 // ------------------------------------------------------------------------------------------
 // modular arithmetic
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q) { return x * w - __umulhi(x, ws) * Q; } // [0,2Q)
+// Both parameter sets of the reference share Q = PreviousPrime(FirstPrime(27, 2N), 2N) = 2^27 - 2^11 + 1.  For that
+// modulus t*Q mod 2^32 = t - ((t - (t << 16)) << 11): three ALU-pipe instructions instead of one IMAD on the FMA-heavy
+// pipe, which is the unit that bounds the kernel (profiles/r1_blind_rotate_ncu_summary.md).  bfhe_create refuses any other
+// modulus when this is compiled in; build with -DBFHE_GENERIC_Q for the plain form.
+#ifndef BFHE_GENERIC_Q
+#define BFHE_SOLINAS_Q 1
+__device__ __forceinline__ u32 mul_q(u32 t, u32) { return t - ((t - (t << 16)) << 11); }
+#else
+#define BFHE_SOLINAS_Q 0
+__device__ __forceinline__ u32 mul_q(u32 t, u32 Q) { return t * Q; }
+#endif
+bool kernels_built_for_solinas_q() { return BFHE_SOLINAS_Q != 0; }
+__device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q) { // [0,2Q)
+#if BFHE_SOLINAS_Q
+  const u32 t = __umulhi(x, ws);
+  const u32 s = t - (t << 16);
+  return (x * w - t) + (s << 11); // x*w - t*Q
+#else
+  return x * w - __umulhi(x, ws) * Q;
+#endif
+}
 __device__ __forceinline__ u32 redc(u64 s, u32 Q, u32 qinv_neg) { // s * 2^-32 mod Q, lazy
   u32 m = (u32)s * qinv_neg;
   return (u32)((s + (u64)m * Q) >> 32);
 }
-__device__ __forceinline__ u32 lazy_reduce(u32 x, u32 Q, u32 mu) { return x - __umulhi(x, mu) * Q; } // any x -> [0,2Q)
+__device__ __forceinline__ u32 lazy_reduce(u32 x, u32 Q, u32 mu) { // any x -> [0,2Q)
+#if BFHE_SOLINAS_Q
+  const u32 t = x >> 27; // floor(2^32 / Q) = 32, so the Barrett quotient estimate is a shift
+  return x - mul_q(t, Q);
+#else
+  return x - __umulhi(x, mu) * Q;
+#endif
+}
 __device__ __forceinline__ u32 csub(u32 x, u32 Q) { return min(x, x - Q); }                            // [0,2Q) -> [0,Q)
 
 // ------------------------------------------------------------------------------------------
@@ -222,7 +249,7 @@ __device__ __forceinline__ u32 brev(u32 x, int bits) { return __brev(x) >> (32 -
 template <int LOGN, int DG, int LOGBG, int G, bool AP> struct BrCfg {
   static constexpr int N = 1 << LOGN, E = N / 32, C = E / 4, ROWS = 2 * DG;
   static constexpr int W = 2 * G, THREADS = 32 * W;
-  static constexpr int NPAD = 1024; // per-gate index table (>= n*dR)
+  static constexpr int NPAD = AP ? 1024 : 512; // per-gate index table (>= n*dR for AP, >= n for GINX)
   static constexpr size_t dct_words = (size_t)G * ROWS * N;
   static constexpr size_t smem_bytes = (dct_words + 4 * N + (AP ? 0 : 2 * N)) * 4 + (size_t)G * NPAD * 2;
 };
@@ -339,13 +366,25 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
       }
     }
     pending = pending || active;
+    // GINX: this warp's first key chunk is requested BEFORE the barrier, so the L2 round trip overlaps the wait for
+    // the slower warps of the CTA instead of stalling the external product (ncu r1: 6 % of samples sat on these loads)
+    uint4 kr[AP ? 1 : 2][ROWS][2];
+    if (!AP && warp < C * GS) {
+      const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + ((warp % C) * 32 + lane) * 4;
+#pragma unroll
+      for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int r = 0; r < ROWS; r++)
+#pragma unroll
+          for (int cc = 0; cc < 2; cc++)
+            kr[s][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((s * ROWS + r) * 2 + cc) * N));
+    }
     __syncthreads();
 
     // ================= phase B: external product, slot-parallel over the CTA =================
     for (int item = warp; item < C * GS; item += W) {
       const int qc = item % C, gs0 = item / C;
-      uint4 kr[AP ? 1 : 2][ROWS][2];
-      if (!AP) {
+      if (!AP && item != warp) { // further chunks of this warp (fewer warps than chunks)
         const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + (qc * 32 + lane) * 4;
 #pragma unroll
         for (int s = 0; s < 2; s++)
@@ -757,6 +796,10 @@ static int launch_br_g(int G, const DevConst &P, const DevGate *d_gates, int cou
   switch (G) {
   case 1: return launch_br_inst<LOGN, DG, LOGBG, 1, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
   case 2: return launch_br_inst<LOGN, DG, LOGBG, 2, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
+  case 5:
+    if constexpr (LOGN == 10 && !AP) return launch_br_inst<LOGN, DG, LOGBG, 5, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
+  case 6:
+    if constexpr (LOGN == 10 && !AP) return launch_br_inst<LOGN, DG, LOGBG, 6, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
   default: return launch_br_inst<LOGN, DG, LOGBG, 4, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
   }
 }
@@ -789,7 +832,7 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // narrow wavefront (fewer than 4 gates per SM): the latency variant -- one gate per CTA, one warp per digit row;
   // wide wavefront: the throughput variant -- G gates per CTA share every bootstrapping-key word
-  const bool lat = force_g == 8 || (force_g == 0 && count <= 4 * sms);
+  const bool lat = force_g == 8 || (force_g == 0 && count <= sms + sms / 2);
   if (lat) {
     if (P.N == 1024 && P.dG == 4 && P.logBG == 7)
       return method_ap ? launch_lat_inst<10, 4, 7, true>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
@@ -799,7 +842,7 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
                        : launch_lat_inst<9, 3, 9, false>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);
     return (int)cudaErrorInvalidValue;
   }
-  int G = force_g > 0 ? force_g : 4;
+  int G = force_g > 0 ? force_g : (count <= 2 * sms ? 2 : 4);
   if (P.N == 1024 && P.dG == 4 && P.logBG == 7) {
     return method_ap ? launch_br_g<10, 4, 7, true>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
                      : launch_br_g<10, 4, 7, false>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);
