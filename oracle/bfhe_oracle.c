@@ -235,42 +235,48 @@ static inline u32 mul_shoup(u32 x, u32 w, u32 wsh, u32 Q) {
   return r - (Q & -(u32)(r >= Q));
 }
 /* Cooley-Tukey, natural in, bit-reversed out: slot j = a(psi^(2*br(j)+1)) */
-void orc_ntt_fwd(const orc_ctx *c, u32 *a) {
-  u32 N = c->p.N, Q = (u32)c->p.Q;
+void orc_ntt_fwd(const orc_ctx *c, u32 *restrict a) {
+  const u32 N = c->p.N, Q = (u32)c->p.Q;
+  const u32 *restrict tw = c->tw, *restrict tws = c->tw_sh;
   u32 t = N;
   for (u32 m = 1; m < N; m <<= 1) {
     t >>= 1;
     for (u32 i = 0; i < m; i++) {
-      u32 w = c->tw[m + i], ws = c->tw_sh[m + i], j1 = 2 * i * t;
-      for (u32 j = j1; j < j1 + t; j++) {
-        u32 u = a[j], v = mul_shoup(a[j + t], w, ws, Q);
-        u32 s = u + v;
-        a[j] = s - (Q & -(u32)(s >= Q));
-        a[j + t] = u - v + (Q & -(u32)(u < v));
+      const u32 w = tw[m + i], ws = tws[m + i];
+      u32 *restrict lo = a + 2 * i * t, *restrict hi = lo + t;
+#pragma omp simd
+      for (u32 j = 0; j < t; j++) {
+        const u32 u = lo[j], v = mul_shoup(hi[j], w, ws, Q);
+        const u32 s = u + v;
+        lo[j] = s - (Q & -(u32)(s >= Q));
+        hi[j] = u - v + (Q & -(u32)(u < v));
       }
     }
   }
 }
 /* Gentleman-Sande, bit-reversed in, natural out, times N^-1 */
-void orc_ntt_inv(const orc_ctx *c, u32 *a) {
-  u32 N = c->p.N, Q = (u32)c->p.Q;
+void orc_ntt_inv(const orc_ctx *c, u32 *restrict a) {
+  const u32 N = c->p.N, Q = (u32)c->p.Q;
+  const u32 *restrict tw = c->itw, *restrict tws = c->itw_sh;
   u32 t = 1;
   for (u32 m = N; m > 1; m >>= 1) {
-    u32 h = m >> 1, j1 = 0;
+    const u32 h = m >> 1;
     for (u32 i = 0; i < h; i++) {
-      u32 w = c->itw[h + i], ws = c->itw_sh[h + i];
-      for (u32 j = j1; j < j1 + t; j++) {
-        u32 u = a[j], v = a[j + t];
-        u32 s = u + v;
-        a[j] = s - (Q & -(u32)(s >= Q));
-        u32 d = u - v + (Q & -(u32)(u < v));
-        a[j + t] = mul_shoup(d, w, ws, Q);
+      const u32 w = tw[h + i], ws = tws[h + i];
+      u32 *restrict lo = a + 2 * i * t, *restrict hi = lo + t;
+#pragma omp simd
+      for (u32 j = 0; j < t; j++) {
+        const u32 u = lo[j], v = hi[j];
+        const u32 s = u + v;
+        lo[j] = s - (Q & -(u32)(s >= Q));
+        const u32 d = u - v + (Q & -(u32)(u < v));
+        hi[j] = mul_shoup(d, w, ws, Q);
       }
-      j1 += 2 * t;
     }
     t <<= 1;
   }
-  u32 ninv = (u32)c->n_inv, nsh = shoup(c->n_inv, Q);
+  const u32 ninv = (u32)c->n_inv, nsh = shoup(c->n_inv, Q);
+#pragma omp simd
   for (u32 j = 0; j < N; j++) a[j] = mul_shoup(a[j], ninv, nsh, Q);
 }
 static inline u32 mulmod32(u32 a, u32 b, u32 Q) { return (u32)((u64)a * b % Q); }
@@ -495,38 +501,47 @@ void orc_prep(const orc_ctx *c, uint32_t op, const uint32_t *ct1, const uint32_t
 
 /* RingGSWAccumulator::SignedDigitDecompose (rgsw-acc.cpp): in = 2 polys (coef), out = 2*dG polys, digit l of poly j -> j+2l */
 void orc_signed_digit_decompose(const orc_ctx *c, const uint32_t *in, uint32_t *out) {
-  u32 N = c->p.N, dG = c->p.dG;
+  const u32 N = c->p.N, dG = c->p.dG; /* dG is 3 (TOY) or 4 (STD128_OPT) */
   /* OpenFHE does this in signed 64-bit; |d| < 2^27 so signed 32-bit gives the same digits */
-  int32_t Q = (int32_t)c->p.Q, QHalf = Q >> 1;
-  int gBits = c->logBG, shift = 32 - gBits;
-  for (u32 j = 0; j < 2; j++)
-    for (u32 l = 0; l < dG; l++) {
-      u32 *o = out + (size_t)(j + 2 * l) * N;
-      const u32 *src = in + (size_t)j * N;
-      for (u32 k = 0; k < N; k++) {
-        int32_t t = (int32_t)src[k];
-        int32_t d = (t < QHalf) ? t : t - Q;
-        int32_t r = 0;
-        for (u32 ll = 0; ll <= l; ll++) { /* peel digits 0..l; digit l is the one stored */
-          r = (int32_t)((u32)d << shift) >> shift; /* signed remainder */
-          d -= r;
-          d >>= gBits;
-        }
-        o[k] = (u32)(r + (Q & (r >> 31)));
-      }
+  const int32_t Q = (int32_t)c->p.Q, QHalf = Q >> 1;
+  const int gBits = c->logBG, shift = 32 - gBits;
+  for (u32 j = 0; j < 2; j++) {
+    const u32 *restrict src = in + (size_t)j * N;
+    u32 *restrict o0 = out + (size_t)(j + 0) * N, *restrict o1 = out + (size_t)(j + 2) * N;
+    u32 *restrict o2 = out + (size_t)(j + 4) * N, *restrict o3 = dG > 3 ? out + (size_t)(j + 6) * N : o2;
+#pragma omp simd
+    for (u32 k = 0; k < N; k++) {
+      const int32_t t = (int32_t)src[k];
+      int32_t d = (t < QHalf) ? t : t - Q;
+      int32_t r;
+      r = (int32_t)((u32)d << shift) >> shift; d -= r; d >>= gBits; /* signed remainder, then exact division */
+      o0[k] = (u32)(r + (Q & (r >> 31)));
+      r = (int32_t)((u32)d << shift) >> shift; d -= r; d >>= gBits;
+      o1[k] = (u32)(r + (Q & (r >> 31)));
+      r = (int32_t)((u32)d << shift) >> shift; d -= r; d >>= gBits;
+      const u32 v2 = (u32)(r + (Q & (r >> 31)));
+      r = (int32_t)((u32)d << shift) >> shift;
+      const u32 v3 = (u32)(r + (Q & (r >> 31)));
+      if (dG > 3) { o2[k] = v2; o3[k] = v3; } else o2[k] = v2;
     }
+  }
 }
 
 /* acc += / = sum_l dct[l] * key[l][c]  helpers */
 static void ext_product(const orc_ctx *c, const u32 *dct, const u32 *key, u32 *res /* 2N eval */) {
   u32 N = c->p.N, rows = 2 * c->p.dG;
-  u64 Q = c->p.Q, mu = c->mu;
-  for (u32 col = 0; col < 2; col++)
-    for (u32 k = 0; k < N; k++) {
-      u64 s = 0; /* 2*dG <= 8 products below 2^54 each: no overflow */
-      for (u32 l = 0; l < rows; l++) s += (u64)dct[(size_t)l * N + k] * key[((size_t)l * 2 + col) * N + k];
-      res[col * N + k] = barrett64(s, Q, mu);
+  const u64 Q = c->p.Q, mu = c->mu;
+  u64 *restrict sum = (u64 *)malloc((size_t)N * 8);
+  for (u32 col = 0; col < 2; col++) {
+    memset(sum, 0, (size_t)N * 8); /* 2*dG <= 8 products below 2^54 each: no overflow */
+    for (u32 l = 0; l < rows; l++) {
+      const u32 *restrict d = dct + (size_t)l * N, *restrict kk = key + ((size_t)l * 2 + col) * N;
+#pragma omp simd
+      for (u32 k = 0; k < N; k++) sum[k] += (u64)d[k] * kk[k];
     }
+    for (u32 k = 0; k < N; k++) res[col * N + k] = barrett64(sum[k], Q, mu);
+  }
+  free(sum);
 }
 
 /* BootstrapGateCore + EvalAcc (GINX: RingGSWAccumulatorCGGI::EvalAcc/AddToAcc; AP: RingGSWAccumulatorDM) */
