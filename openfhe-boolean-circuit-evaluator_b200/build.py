@@ -50,5 +50,17 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(tag, extra_flags):
+    """debug/experiment variant of the library (e.g. -DBFHE_PHASE_TIMING): libbfhe_b200_<tag>.so, never used by the product"""
+    out = os.path.join(HERE, "libbfhe_b200_%s.so" % tag)
+    cmd = [NVCC, "-ccbin", CCBIN, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC,-fopenmp,-O3",
+           "-I", os.path.join(HERE, "..", "include"), "-shared", "-o", out] + list(extra_flags)
+    for s in sources():
+        cmd += (["-x", "cu"] if s.endswith(".cpp") else []) + [s]
+    subprocess.check_call(cmd + ["-lgomp", "-ldl", "-cudart", "static"])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

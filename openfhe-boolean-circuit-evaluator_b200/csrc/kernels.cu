@@ -40,15 +40,27 @@ __device__ __forceinline__ u32 mul_q(u32 t, u32) { return t - ((t - (t << 16)) <
 __device__ __forceinline__ u32 mul_q(u32 t, u32 Q) { return t * Q; }
 #endif
 bool kernels_built_for_solinas_q() { return BFHE_SOLINAS_Q != 0; }
-__device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q) { // [0,2Q)
-#if BFHE_SOLINAS_Q
+// SOL selects where the t*Q term runs: true = three ALU-pipe instructions (shift/add), false = one IMAD on the
+// FMA-heavy pipe.  Both pipes issue 16 lanes/cycle per SM sub-partition, so the kernels mix the two forms per butterfly
+// stage to balance them (masks below).
+template <bool SOL = false> __device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q) { // [0,2Q)
   const u32 t = __umulhi(x, ws);
-  const u32 s = t - (t << 16);
-  return (x * w - t) + (s << 11); // x*w - t*Q
-#else
-  return x * w - __umulhi(x, ws) * Q;
-#endif
+  if constexpr (SOL && BFHE_SOLINAS_Q) {
+    // (written as shifts; nvcc is free to turn them back into IMADs with small constants -- measured fastest that way)
+    const u32 s = t - (t << 16);
+    return (x * w - t) + (s << 11); // x*w - t*Q
+  } else {
+    return x * w - t * Q;
+  }
 }
+// per-pass stage masks (bit i = stage i of the pass uses the ALU form); tuned with tools/perf_g.py / phase_timing.py
+#ifndef BFHE_SOL_THR_WIDE
+#define BFHE_SOL_THR_WIDE 0x17
+#define BFHE_SOL_THR_NARROW 0x0b
+#define BFHE_SOL_LAT_WIDE 0x05
+#define BFHE_SOL_LAT_NARROW 0x0a
+#define BFHE_SOL_LAT_INV 0x00
+#endif
 __device__ __forceinline__ u32 redc(u64 s, u32 Q, u32 qinv_neg) { // s * 2^-32 mod Q, lazy
   u32 m = (u32)s * qinv_neg;
   return (u32)((s + (u64)m * Q) >> 32);
@@ -56,7 +68,7 @@ __device__ __forceinline__ u32 redc(u64 s, u32 Q, u32 qinv_neg) { // s * 2^-32 m
 __device__ __forceinline__ u32 lazy_reduce(u32 x, u32 Q, u32 mu) { // any x -> [0,2Q)
 #if BFHE_SOLINAS_Q
   const u32 t = x >> 27; // floor(2^32 / Q) = 32, so the Barrett quotient estimate is a shift
-  return x - mul_q(t, Q);
+  return x - t * Q;
 #else
   return x - __umulhi(x, mu) * Q;
 #endif
@@ -113,11 +125,13 @@ template <int E> __device__ __forceinline__ void load_lane_tw(const u32 *tab, u3
 // half-size t has E/(2t) groups, group gi uses twiddle number p = E/(2t) + gi of the pass's table.
 // ------------------------------------------------------------------------------------------
 // Cooley-Tukey (forward).  No range correction: x + T and x - T + 2Q grow by 2Q per stage.
-template <int E, bool UNI>
+template <int E, bool UNI, int SOLMASK = 0>
 __device__ __forceinline__ void ct_pass(u32 (&x)[E], const u32 *__restrict__ utw, const u32 *__restrict__ utws,
                                         const u32 (&w)[E], const u32 (&ws)[E], u32 Q, u32 Q2) {
+  int si = 0;
 #pragma unroll
-  for (int t = E / 2; t >= 1; t >>= 1) {
+  for (int t = E / 2; t >= 1; t >>= 1, si++) {
+    const bool sol = (SOLMASK >> si) & 1;
 #pragma unroll
     for (int gi = 0; gi < E / (2 * t); gi++) {
       const int p = E / (2 * t) + gi;
@@ -125,7 +139,7 @@ __device__ __forceinline__ void ct_pass(u32 (&x)[E], const u32 *__restrict__ utw
 #pragma unroll
       for (int j = 0; j < t; j++) {
         const int a = gi * 2 * t + j, b = a + t;
-        u32 T = mul_shoup(x[b], ww, wws, Q);
+        u32 T = sol ? mul_shoup<true>(x[b], ww, wws, Q) : mul_shoup<false>(x[b], ww, wws, Q);
         x[b] = x[a] - T + Q2;
         x[a] = x[a] + T;
       }
@@ -136,7 +150,7 @@ __device__ __forceinline__ void ct_pass(u32 (&x)[E], const u32 *__restrict__ utw
 // Gentleman-Sande (inverse, unscaled).  B = bound of the inputs in units of Q (<= 16).  Sums double
 // per stage; when they would pass 32Q (= just under 2^32) they are pulled back below 2Q with one
 // lazy Barrett step.  Differences go through the Shoup multiply, which accepts any 32-bit input.
-template <int E, int T, int B, bool UNI, int MAXLAST> struct GsRun {
+template <int E, int T, int B, bool UNI, int MAXLAST, int SOLMASK = 0, int SI = 0> struct GsRun {
   static constexpr int NB = 2 * B;
   static constexpr bool LAST = (2 * T >= E);
   static constexpr bool RED = LAST ? (NB > MAXLAST) : (NB > 16); // pull the sums back below 2Q after this stage?
@@ -154,11 +168,11 @@ template <int E, int T, int B, bool UNI, int MAXLAST> struct GsRun {
         const int a = gi * 2 * T + j, b = a + T;
         u32 S = x[a] + x[b];
         u32 D = x[a] - x[b] + off;
-        x[b] = mul_shoup(D, ww, wws, Q);
+        x[b] = mul_shoup<((SOLMASK >> SI) & 1) != 0>(D, ww, wws, Q);
         x[a] = RED ? lazy_reduce(S, Q, mu) : S;
       }
     }
-    if constexpr (!LAST) GsRun<E, 2 * T, OUTB, UNI, MAXLAST>::run(x, utw, utws, w, ws, Q, mu);
+    if constexpr (!LAST) GsRun<E, 2 * T, OUTB, UNI, MAXLAST, SOLMASK, SI + 1>::run(x, utw, utws, w, ws, Q, mu);
   }
 };
 // bound (in units of Q) of the values GsRun<E,1,B0,*,MAXLAST> leaves behind
@@ -181,12 +195,12 @@ struct TwTabs { // shared-memory per-lane twiddle tables, each N words
 
 // forward: x in column layout (index lane+32k, coefficient form, values < Q) -> row layout (index E*lane+j,
 // evaluation form, lazy < (2*logN+1)Q).  buf: N-word smem scratch, left holding garbage.
-template <int LOGN> __device__ __forceinline__ void ntt_forward(u32 (&x)[(1 << LOGN) / 32], u32 *buf, const DevConst &P,
-                                                               const TwTabs &tt, int lane) {
+template <int LOGN, int SOLW = 0, int SOLN = 0>
+__device__ __forceinline__ void ntt_forward(u32 (&x)[(1 << LOGN) / 32], u32 *buf, const DevConst &P, const TwTabs &tt, int lane) {
   constexpr int E = (1 << LOGN) / 32;
   const u32 Q = P.Q, Q2 = P.Q2;
   u32 w[E], ws[E];
-  ct_pass<E, true>(x, P.tw, P.tws, w, ws, Q, Q2);
+  ct_pass<E, true, SOLW>(x, P.tw, P.tws, w, ws, Q, Q2);
   if constexpr (LOGN & 1) { // span-16 stage across lanes (lane bit 4): group index = k, twiddle psi_br[16+k]
     const bool up = lane & 16;
 #pragma unroll
@@ -202,20 +216,20 @@ template <int LOGN> __device__ __forceinline__ void ntt_forward(u32 (&x)[(1 << L
   row_load<E>(buf, x, lane);
   load_lane_tw<E>(tt.fw, w, lane);
   load_lane_tw<E>(tt.fws, ws, lane);
-  ct_pass<E, false>(x, P.tw, P.tws, w, ws, Q, Q2);
+  ct_pass<E, false, SOLN>(x, P.tw, P.tws, w, ws, Q, Q2);
 }
 
 // inverse (unscaled: N * true value; the keys carry N^-1): x in row layout (evaluation form, values < B0*Q)
 // -> column layout, coefficient form, fully reduced to [0,Q).
-template <int LOGN, int B0> __device__ __forceinline__ void ntt_inverse(u32 (&x)[(1 << LOGN) / 32], u32 *buf, const DevConst &P,
-                                                                        const TwTabs &tt, int lane) {
+template <int LOGN, int B0, int SOLN = 0, int SOLW = 0>
+__device__ __forceinline__ void ntt_inverse(u32 (&x)[(1 << LOGN) / 32], u32 *buf, const DevConst &P, const TwTabs &tt, int lane) {
   constexpr int E = (1 << LOGN) / 32;
   const u32 Q = P.Q, mu = P.mu;
   u32 w[E], ws[E];
   load_lane_tw<E>(tt.iw, w, lane);
   load_lane_tw<E>(tt.iws, ws, lane);
   constexpr int ML = (LOGN & 1) ? 8 : 16; // what the next stage can take
-  GsRun<E, 1, B0, false, ML>::run(x, P.itw, P.itws, w, ws, Q, mu);
+  GsRun<E, 1, B0, false, ML, SOLN>::run(x, P.itw, P.itws, w, ws, Q, mu);
   constexpr int B1 = gs_out_bound(E, B0, ML);
   __syncwarp();
   row_store<E>(buf, x, lane);
@@ -233,9 +247,9 @@ template <int LOGN, int B0> __device__ __forceinline__ void ntt_inverse(u32 (&x)
       x[k] = up ? mul_shoup(D, P.itw[16 + k], P.itws[16 + k], Q) : (x[k] + o);
     }
     constexpr int B2 = 2 * B1;
-    GsRun<E, 1, B2, true, 32>::run(x, P.itw, P.itws, w, ws, Q, mu);
+    GsRun<E, 1, B2, true, 32, SOLW>::run(x, P.itw, P.itws, w, ws, Q, mu);
   } else {
-    GsRun<E, 1, B1, true, 32>::run(x, P.itw, P.itws, w, ws, Q, mu);
+    GsRun<E, 1, B1, true, 32, SOLW>::run(x, P.itw, P.itws, w, ws, Q, mu);
   }
 #pragma unroll
   for (int k = 0; k < E; k++) x[k] = csub(lazy_reduce(x[k], Q, mu), Q);
@@ -245,6 +259,11 @@ template <int LOGN, int B0> __device__ __forceinline__ void ntt_inverse(u32 (&x)
 // blind rotation
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ u32 brev(u32 x, int bits) { return __brev(x) >> (32 - bits); }
+template <int DG, int LOGBG> constexpr u32 digit_offset() { // (B/2) * (1 + B + ... + B^(DG-1))
+  u32 off = 0;
+  for (int l = 0; l < DG; l++) off += (1u << (LOGBG - 1)) << (LOGBG * l);
+  return off;
+}
 
 template <int LOGN, int DG, int LOGBG, int G, bool AP> struct BrCfg {
   static constexpr int N = 1 << LOGN, E = N / 32, C = E / 4, ROWS = 2 * DG;
@@ -261,6 +280,7 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
                     u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
   using Cfg = BrCfg<LOGN, DG, LOGBG, G, AP>;
   constexpr int N = Cfg::N, E = Cfg::E, C = Cfg::C, ROWS = Cfg::ROWS, W = Cfg::W, NPAD = Cfg::NPAD;
+  constexpr u32 DIGIT_OFF = digit_offset<DG, LOGBG>();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   u32 *dct = reinterpret_cast<u32 *>(smem_raw);                 // [G][ROWS][N]
   u32 *s_tw = dct + Cfg::dct_words;                             // fw | fws | iw | iws
@@ -343,25 +363,28 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
       if (pending) {
         u32 x[E];
         row_load<E>(mybuf, x, lane);
-        ntt_inverse<LOGN, AP ? 8 : 4>(x, mybuf, P, tt, lane);
+        ntt_inverse<LOGN, AP ? 8 : 4, BFHE_SOL_THR_NARROW, BFHE_SOL_THR_WIDE>(x, mybuf, P, tt, lane);
 #pragma unroll
         for (int k = 0; k < E; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
       }
       // SignedDigitDecompose (a12): centre, peel DG signed base-2^LOGBG digits, digit l of component c -> row c+2l
-      i32 d[E];
+      // Closed form of the sequential peel (r = signed low digit; d = (d - r) >> LOGBG): adding B/2 at every digit
+      // position turns the balanced digits into the plain base-B digits of d + OFF, so digit l is one shift, one mask and
+      // one subtraction with no dependency on the digits below it (the top digit wraps exactly like the reference's
+      // sign-truncation when dG digits do not cover the centred range, e.g. TOY).
+      u32 dp[E];
 #pragma unroll
-      for (int k = 0; k < E; k++) d[k] = (acc[k] < (Q >> 1)) ? (i32)acc[k] : (i32)acc[k] - (i32)Q;
+      for (int k = 0; k < E; k++) dp[k] = ((acc[k] < (Q >> 1)) ? acc[k] : acc[k] - Q) + DIGIT_OFF;
 #pragma unroll
       for (int l = 0; l < DG; l++) {
         u32 x[E];
 #pragma unroll
         for (int k = 0; k < E; k++) {
-          i32 r = (i32)((u32)d[k] << (32 - LOGBG)) >> (32 - LOGBG);
-          d[k] = (d[k] - r) >> LOGBG;
-          x[k] = min((u32)r, (u32)r + Q);
+          const u32 r = ((dp[k] >> (LOGBG * l)) & ((1u << LOGBG) - 1)) - (1u << (LOGBG - 1));
+          x[k] = min(r, r + Q);
         }
         u32 *buf = dct + ((size_t)g * ROWS + c + 2 * l) * N;
-        ntt_forward<LOGN>(x, buf, P, tt, lane);
+        ntt_forward<LOGN, BFHE_SOL_THR_WIDE, BFHE_SOL_THR_NARROW>(x, buf, P, tt, lane);
         row_store<E>(buf, x, lane);
       }
     }
@@ -464,7 +487,7 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
     if (pending) {
       u32 x[E];
       row_load<E>(mybuf, x, lane);
-      ntt_inverse<LOGN, AP ? 8 : 4>(x, mybuf, P, tt, lane);
+      ntt_inverse<LOGN, AP ? 8 : 4, BFHE_SOL_THR_NARROW, BFHE_SOL_THR_WIDE>(x, mybuf, P, tt, lane);
 #pragma unroll
       for (int k = 0; k < E; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
     }
@@ -536,6 +559,7 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
                         u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
   using Cfg = LatCfg<LOGN, DG, LOGBG, AP>;
   constexpr int N = Cfg::N, E = Cfg::E, C = Cfg::C, ROWS = Cfg::ROWS, W = Cfg::W, NPAD = Cfg::NPAD, KEYPOLYS = Cfg::KEYPOLYS;
+  constexpr u32 DIGIT_OFF = digit_offset<DG, LOGBG>();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   u32 *dct = reinterpret_cast<u32 *>(smem_raw);         // [ROWS][N]
   u32 *dig = dct + (size_t)ROWS * N;                    // [2][N] packed signed digits of the accumulator
@@ -626,8 +650,14 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     }
   }
   const u32 eA = 2 * brev(lane, 5) + 1;
-  constexpr u32 FIELD = LOGBG; // packed digit field width: DG * LOGBG <= 32
 
+#ifdef BFHE_PHASE_TIMING
+  long long tph[5] = {0, 0, 0, 0, 0}, tc0, tc1;
+#define PH_T(i) do { tc1 = clock64(); tph[i] += tc1 - tc0; tc0 = tc1; } while (0)
+  tc0 = clock64();
+#else
+#define PH_T(i)
+#endif
   for (int j = 0; j < nact; j++) {
     const int step = s_list[j];
     // ---- phase 1: warps 0,1 close the previous step (INTT, accumulate) and decompose ----
@@ -636,40 +666,34 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
         u32 x[E];
         u32 *rb = dct + (size_t)warp * N;
         row_load<E>(rb, x, lane);
-        ntt_inverse<LOGN, AP ? 8 : 4>(x, rb, P, tt, lane);
+        ntt_inverse<LOGN, AP ? 8 : 4, BFHE_SOL_LAT_INV, BFHE_SOL_LAT_INV>(x, rb, P, tt, lane);
 #pragma unroll
         for (int k = 0; k < E; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
       }
+      // centred accumulator + digit offset: every warp then cuts its own digit out with a shift and a mask
 #pragma unroll
-      for (int k = 0; k < E; k++) {
-        i32 d = (acc[k] < (Q >> 1)) ? (i32)acc[k] : (i32)acc[k] - (i32)Q;
-        u32 packed = 0;
-#pragma unroll
-        for (int ll = 0; ll < DG; ll++) {
-          const i32 r = (i32)((u32)d << (32 - LOGBG)) >> (32 - LOGBG);
-          d = (d - r) >> LOGBG;
-          packed |= ((u32)r & ((1u << FIELD) - 1)) << (FIELD * ll);
-        }
-        dig[warp * N + lane + 32 * k] = packed;
-      }
+      for (int k = 0; k < E; k++) dig[warp * N + lane + 32 * k] = ((acc[k] < (Q >> 1)) ? acc[k] : acc[k] - Q) + DIGIT_OFF;
     }
+    PH_T(0);
     __syncthreads();
+    PH_T(1);
     // ---- phase 2: every warp transforms its own digit polynomial ----
     {
       u32 x[E];
 #pragma unroll
       for (int k = 0; k < E; k++) {
-        const u32 pk = dig[c * N + lane + 32 * k];
-        const i32 r = (i32)(pk << (32 - FIELD * (l + 1))) >> (32 - FIELD);
-        x[k] = min((u32)r, (u32)r + Q);
+        const u32 r = ((dig[c * N + lane + 32 * k] >> (LOGBG * l)) & ((1u << LOGBG) - 1)) - (1u << (LOGBG - 1));
+        x[k] = min(r, r + Q);
       }
       u32 *buf = dct + (size_t)warp * N;
-      ntt_forward<LOGN>(x, buf, P, tt, lane);
+      ntt_forward<LOGN, BFHE_SOL_LAT_WIDE, BFHE_SOL_LAT_NARROW>(x, buf, P, tt, lane);
       row_store<E>(buf, x, lane);
     }
+    PH_T(2);
     __syncthreads();
-    // ---- phase 3: external product against the staged key tile ----
     mbar_wait(s_bar, (u32)(j & 1));
+    PH_T(3);
+    // ---- phase 3: external product against the staged key tile ----
     for (int qc = warp; qc < C; qc += W) {
       u32 fp[4], fn[4];
       if (!AP) {
@@ -713,6 +737,7 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
         *reinterpret_cast<uint4 *>(gd + (size_t)cc * N) = make_uint4(out[0], out[1], out[2], out[3]);
       }
     }
+    PH_T(4);
     __syncthreads();
     // ---- prefetch the next step's key tile while the next transforms run ----
     if (tid == 0 && j + 1 < nact) {
@@ -730,7 +755,7 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
       u32 x[E];
       u32 *rb = dct + (size_t)warp * N;
       row_load<E>(rb, x, lane);
-      ntt_inverse<LOGN, AP ? 8 : 4>(x, rb, P, tt, lane);
+      ntt_inverse<LOGN, AP ? 8 : 4, BFHE_SOL_LAT_INV, BFHE_SOL_LAT_INV>(x, rb, P, tt, lane);
 #pragma unroll
       for (int k = 0; k < E; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
     }
@@ -738,6 +763,10 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
 #pragma unroll
       for (int k = 0; k < E; k++) acc_dbg[(gi * 2 + warp) * N + lane + 32 * k] = acc[k];
     }
+#ifdef BFHE_PHASE_TIMING
+    if (acc_dbg && lane == 0)
+      for (int i = 0; i < 5; i++) acc_dbg[(gi * 2 + warp) * N + 32 + i] = (u32)(tph[i] / 1000); // kilo-cycles
+#endif
     u32 *e = ext + gi * (N + 4);
     const u64 qKS = P.qKS;
     if (warp == 0) {

@@ -3,6 +3,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bfhe_loader
 B = bfhe_loader.load_package()
+if os.environ.get('BFHE_LIB'):
+    B.LIB_PATH = os.path.join(os.path.dirname(B.LIB_PATH), os.environ['BFHE_LIB'])
 ctx = B.Context(B.STD128_OPT, B.GINX, 0)
 ctx.keygen(1); ctx.btkeygen(2)
 n_in = 4096

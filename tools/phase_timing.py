@@ -1,0 +1,21 @@
+"""Per-phase cycle breakdown of the latency kernel (debug build with -DBFHE_PHASE_TIMING)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bfhe_loader
+B = bfhe_loader.load_package()
+if os.environ.get('BFHE_LIB'):
+    B.LIB_PATH = os.path.join(os.path.dirname(B.LIB_PATH), os.environ['BFHE_LIB'])
+ctx = B.Context(B.STD128_OPT, B.GINX, 0)
+ctx.keygen(1); ctx.btkeygen(2)
+for count in (1, 148):
+    bits = np.random.default_rng(0).integers(0, 2, 2 * count)
+    slab = ctx.slab(3 * count); slab.upload(ctx.encrypt(bits, seed=1))
+    g = np.zeros(count, dtype=B.GATE_DTYPE)
+    g["op"] = B.NAND; g["in0"] = 2 * np.arange(count); g["in1"] = 2 * np.arange(count) + 1; g["out"] = 2 * count + np.arange(count)
+    ctx.dbg_set_gates_per_cta(8)
+    acc = ctx.dbg_blind_rotate(slab, g)
+    t = acc[:, :, 32:37].astype(np.float64)  # kilo-cycles per phase, warps 0 and 1
+    names = ["intt+decompose", "barrier1", "ntt", "barrier2+keywait", "mac"]
+    for w in (0, 1):
+        print(count, "gates, warp", w, {n: round(float(v), 1) for n, v in zip(names, t[:, w].mean(0))}, "total kcyc", round(float(t[:, w].sum(1).mean()), 1))
