@@ -514,6 +514,72 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
 }
 
 
+
+// ------------------------------------------------------------------------------------------
+// inverse transform spread over 4 warps (N = 1024): every lane holds 8 values instead of 32, so the serial chain
+// per thread is 4x shorter; the two widest stages of each pass run across lanes with warp shuffles
+// (lane ^ 1, lane ^ 2).  Used by the latency kernel, where only two polynomials need an INTT per step and all
+// eight warps would otherwise wait for two of them.  Warp q4 of the group handles rows (pass A) / columns (pass B)
+// 8*q4 .. 8*q4+7; lane = 4*(row or column within the warp) + s, s = which quarter of the 32 points.
+// ------------------------------------------------------------------------------------------
+template <int B> __device__ __forceinline__ void gs_shuffle_stage(u32 (&x)[8], int mask, bool up, u32 w, u32 ws, u32 Q) {
+  static_assert(B <= 16, "bound");
+  const u32 off = B * Q;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const u32 o = __shfl_xor_sync(0xffffffffu, x[j], mask);
+    const u32 D = o - x[j] + off;          // upper lane: U - V (U arrives from the lower lane)
+    x[j] = up ? mul_shoup(D, w, ws, Q) : (x[j] + o);
+  }
+}
+template <int B0>
+__device__ __forceinline__ void ntt_inverse_quad(u32 (&x)[8], u32 *buf, const DevConst &P, const TwTabs &tt, const u32 *s_uitw,
+                                                 int q4, int lane, int bar_id) {
+  constexpr int E = 32;
+  const u32 Q = P.Q, mu = P.mu;
+  const int r8 = lane >> 2, s = lane & 3, line = 8 * q4 + r8;
+  u32 wl[8], wsl[8];
+  // ---- pass A: row `line`, points j = 8s .. 8s+7 (spans 1, 2, 4 in registers; 8, 16 across lanes) ----
+  {
+    const uint4 a = *reinterpret_cast<const uint4 *>(buf + Lay<E>::chunk_off(line, 2 * s));
+    const uint4 b = *reinterpret_cast<const uint4 *>(buf + Lay<E>::chunk_off(line, 2 * s + 1));
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  }
+  auto ld = [&](const u32 *tab, int chunk) { return reinterpret_cast<const uint4 *>(tab)[chunk * 32 + line]; };
+  const uint4 c0 = ld(tt.iw, 0), c0s = ld(tt.iws, 0), c1 = ld(tt.iw, 1), c1s = ld(tt.iws, 1);
+  const uint4 c2 = ld(tt.iw, 2 + (s >> 1)), c2s = ld(tt.iws, 2 + (s >> 1)), c4 = ld(tt.iw, 4 + s), c4s = ld(tt.iws, 4 + s);
+  wl[4] = c4.x; wl[5] = c4.y; wl[6] = c4.z; wl[7] = c4.w;      // span 1: twiddle 16 + 4s + g
+  wsl[4] = c4s.x; wsl[5] = c4s.y; wsl[6] = c4s.z; wsl[7] = c4s.w;
+  wl[2] = (s & 1) ? c2.z : c2.x; wl[3] = (s & 1) ? c2.w : c2.y; // span 2: twiddle 8 + 2s + g
+  wsl[2] = (s & 1) ? c2s.z : c2s.x; wsl[3] = (s & 1) ? c2s.w : c2s.y;
+  wl[1] = s == 0 ? c1.x : s == 1 ? c1.y : s == 2 ? c1.z : c1.w;   // span 4: twiddle 4 + s
+  wsl[1] = s == 0 ? c1s.x : s == 1 ? c1s.y : s == 2 ? c1s.z : c1s.w;
+  wl[0] = wsl[0] = 0;
+  GsRun<8, 1, B0, false, 16>::run(x, nullptr, nullptr, wl, wsl, Q, mu);
+  constexpr int BA = gs_out_bound(8, B0, 16);
+  gs_shuffle_stage<BA>(x, 1, s & 1, (s >> 1) ? c0.w : c0.z, (s >> 1) ? c0s.w : c0s.z, Q); // span 8: twiddle 2 + (s>>1)
+  gs_shuffle_stage<2 * BA>(x, 2, s & 2, c0.y, c0s.y, Q);                                   // span 16: twiddle 1
+  constexpr int BA3 = 4 * BA;
+  *reinterpret_cast<uint4 *>(buf + Lay<E>::chunk_off(line, 2 * s)) = make_uint4(x[0], x[1], x[2], x[3]);
+  *reinterpret_cast<uint4 *>(buf + Lay<E>::chunk_off(line, 2 * s + 1)) = make_uint4(x[4], x[5], x[6], x[7]);
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+  // ---- pass B: column `line`, points k = 8s .. 8s+7 (index line + 32k; spans 32, 64, 128 in registers; 256, 512 across lanes) ----
+#pragma unroll
+  for (int kk = 0; kk < 8; kk++) x[kk] = buf[Lay<E>::elem_off(8 * s + kk, line)];
+#pragma unroll
+  for (int g = 0; g < 4; g++) { wl[4 + g] = s_uitw[16 + 4 * s + g]; wsl[4 + g] = s_uitw[32 + 16 + 4 * s + g]; }
+#pragma unroll
+  for (int g = 0; g < 2; g++) { wl[2 + g] = s_uitw[8 + 2 * s + g]; wsl[2 + g] = s_uitw[32 + 8 + 2 * s + g]; }
+  wl[1] = s_uitw[4 + s]; wsl[1] = s_uitw[32 + 4 + s];
+  GsRun<8, 1, BA3, false, 16>::run(x, nullptr, nullptr, wl, wsl, Q, mu);
+  constexpr int BB = gs_out_bound(8, BA3, 16);
+  gs_shuffle_stage<BB>(x, 1, s & 1, s_uitw[2 + (s >> 1)], s_uitw[32 + 2 + (s >> 1)], Q);
+  gs_shuffle_stage<(2 * BB > 16 ? 16 : 2 * BB)>(x, 2, s & 2, s_uitw[1], s_uitw[33], Q);
+  static_assert(2 * BB <= 16, "bound");
+#pragma unroll
+  for (int kk = 0; kk < 8; kk++) x[kk] = csub(lazy_reduce(x[kk], Q, mu), Q);
+}
+
 // ------------------------------------------------------------------------------------------
 // blind rotation, latency variant: ONE gate per CTA, one warp per decomposition row (2*DG warps), so the 2*DG
 // forward NTTs of a step run concurrently and the step's critical path is INTT -> NTT -> MAC instead of
@@ -570,6 +636,8 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   u16 *s_list = s_idx + NPAD;                           // [NPAD] steps that do work
   u64 *s_bar = reinterpret_cast<u64 *>(s_list + NPAD);
   __shared__ u32 s_b, s_nact;
+  __shared__ u32 s_uitw[64]; // uniform inverse twiddles (itw | itws) for lane-dependent lookups of the 4-warp INTT
+  constexpr bool QUAD = (LOGN == 10 && W == 8); // INTT spread over 4 warps per polynomial
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = warp & 1, l = warp >> 1; // this warp transforms digit l of accumulator component c (row c + 2l)
@@ -581,6 +649,7 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   if (!AP)
     for (int i = tid; i < 2 * N; i += Cfg::THREADS) s_psiM[i] = g_psiM[i];
   const TwTabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
+  if (tid < 32) { s_uitw[tid] = P.itw[tid]; s_uitw[32 + tid] = P.itws[tid]; }
   if (tid == 0) {
     mbar_init(s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -631,17 +700,19 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     for (u32 off = 0; off < KEYBYTES; off += 16384) bulk_g2s(reinterpret_cast<char *>(s_key) + off, reinterpret_cast<const char *>(src) + off, min(16384u, KEYBYTES - off), s_bar);
   }
 
-  // accumulator (coefficient form) lives in the registers of warps 0 and 1
-  u32 acc[E];
+  // accumulator (coefficient form).  QUAD: 8 coefficients per thread, component qc = warp / 4, index qL + 32 * (8 * qs + kk);
+  // otherwise 32 coefficients per lane in warps 0 and 1 (component = warp, index lane + 32k).
+  const int qc = warp >> 2, q4 = warp & 3, qL = 8 * q4 + (lane >> 2), qs = lane & 3;
+  u32 acc[QUAD ? 8 : E];
 #pragma unroll
-  for (int k = 0; k < E; k++) acc[k] = 0;
-  if (warp == 1) {
+  for (int k = 0; k < (QUAD ? 8 : E); k++) acc[k] = 0;
+  if (QUAD ? (qc == 1) : (warp == 1)) {
     const u32 gate = dg.op & 0xff;
     const u32 q1 = P.gate_const[gate == OP_BOOTSTRAP ? OP_AND : gate], q2 = (q1 + q / 2) % q;
     const u32 b = s_b, Q8 = P.Q8, Q8n = Q - P.Q8;
 #pragma unroll
-    for (int k = 0; k < E; k++) {
-      const u32 idx = lane + 32 * k;
+    for (int k = 0; k < (QUAD ? 8 : E); k++) {
+      const u32 idx = QUAD ? (u32)(qL + 32 * (8 * qs + k)) : (u32)(lane + 32 * k);
       if (idx % P.factor == 0) {
         const u32 t = (b + q - idx / P.factor) % q;
         const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
@@ -660,8 +731,17 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
 #endif
   for (int j = 0; j < nact; j++) {
     const int step = s_list[j];
-    // ---- phase 1: warps 0,1 close the previous step (INTT, accumulate) and decompose ----
-    if (warp < 2) {
+    // ---- phase 1: close the previous step (INTT, accumulate) and publish the centred accumulator + digit offset ----
+    if constexpr (QUAD) {
+      if (j > 0) {
+        u32 x[8];
+        ntt_inverse_quad<AP ? 8 : 4>(x, dct + (size_t)qc * N, P, tt, s_uitw, q4, lane, 1 + qc);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) dig[qc * N + qL + 32 * (8 * qs + k)] = ((acc[k] < (Q >> 1)) ? acc[k] : acc[k] - Q) + DIGIT_OFF;
+    } else if (warp < 2) {
       if (j > 0) {
         u32 x[E];
         u32 *rb = dct + (size_t)warp * N;
@@ -750,7 +830,28 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   }
 
   // ---- epilogue ----
-  if (warp < 2) {
+  const u64 qKS = P.qKS;
+  u32 *e = ext + gi * (N + 4);
+  auto modswitch = [&](u32 v) -> u32 { return (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS); };
+  if constexpr (QUAD) {
+    if (nact > 0) {
+      u32 x[8];
+      ntt_inverse_quad<AP ? 8 : 4>(x, dct + (size_t)qc * N, P, tt, s_uitw, q4, lane, 1 + qc);
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const u32 jj = qL + 32 * (8 * qs + k);
+      if (acc_dbg) acc_dbg[(gi * 2 + qc) * N + jj] = acc[k];
+      if (qc == 0) {
+        const u32 v = (jj == 0) ? acc[k] : (acc[k] == 0 ? 0 : Q - acc[k]); // a'_0 = a_0, a'_k = -a_{N-k}
+        e[(jj == 0) ? 0 : N - jj] = modswitch(v);
+      } else if (jj == 0) {
+        e[N] = modswitch(csub(acc[k] + P.Q8, Q));
+      }
+    }
+  } else if (warp < 2) {
     if (nact > 0) {
       u32 x[E];
       u32 *rb = dct + (size_t)warp * N;
@@ -763,25 +864,21 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
 #pragma unroll
       for (int k = 0; k < E; k++) acc_dbg[(gi * 2 + warp) * N + lane + 32 * k] = acc[k];
     }
-#ifdef BFHE_PHASE_TIMING
-    if (acc_dbg && lane == 0)
-      for (int i = 0; i < 5; i++) acc_dbg[(gi * 2 + warp) * N + 32 + i] = (u32)(tph[i] / 1000); // kilo-cycles
-#endif
-    u32 *e = ext + gi * (N + 4);
-    const u64 qKS = P.qKS;
     if (warp == 0) {
 #pragma unroll
       for (int k = 0; k < E; k++) {
         const u32 jj = lane + 32 * k;
         const u32 v = (jj == 0) ? acc[k] : (acc[k] == 0 ? 0 : Q - acc[k]);
-        const u32 pos = (jj == 0) ? 0 : N - jj;
-        e[pos] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+        e[(jj == 0) ? 0 : N - jj] = modswitch(v);
       }
     } else if (lane == 0) {
-      const u32 v = csub(acc[0] + P.Q8, Q);
-      e[N] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+      e[N] = modswitch(csub(acc[0] + P.Q8, Q));
     }
   }
+#ifdef BFHE_PHASE_TIMING
+  if (acc_dbg && lane == 0 && (QUAD ? (q4 == 0) : (warp < 2)))
+    for (int i = 0; i < 5; i++) acc_dbg[(gi * 2 + (QUAD ? qc : warp)) * N + 32 + i] = (u32)(tph[i] / 1000); // kilo-cycles
+#endif
 }
 
 template <int LOGN, int DG, int LOGBG, bool AP>
