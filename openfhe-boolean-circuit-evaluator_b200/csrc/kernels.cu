@@ -125,17 +125,33 @@ template <int E> __device__ __forceinline__ void load_lane_tw(const u32 *tab, u3
 // half-size t has E/(2t) groups, group gi uses twiddle number p = E/(2t) + gi of the pass's table.
 // ------------------------------------------------------------------------------------------
 // Cooley-Tukey (forward).  No range correction: x + T and x - T + 2Q grow by 2Q per stage.
-template <int E, bool UNI, int SOLMASK = 0>
+// STREAM: the per-lane twiddles are read from the shared-memory table chunk by chunk as the stages need them (at
+// most 8 registers live) instead of being preloaded into 2*E registers -- what lets 12 warps per SM fit the register file.
+#ifndef BFHE_STREAM_TW
+#define BFHE_STREAM_TW 1
+#endif
+__device__ __forceinline__ u32 comp4(const uint4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+template <int E, bool UNI, int SOLMASK = 0, bool STREAM = false>
 __device__ __forceinline__ void ct_pass(u32 (&x)[E], const u32 *__restrict__ utw, const u32 *__restrict__ utws,
-                                        const u32 (&w)[E], const u32 (&ws)[E], u32 Q, u32 Q2) {
+                                        const u32 (&w)[E], const u32 (&ws)[E], u32 Q, u32 Q2, const u32 *tab = nullptr,
+                                        const u32 *tabs = nullptr, int lane = 0) {
   int si = 0;
+  uint4 cw = make_uint4(0, 0, 0, 0), cws = cw;
 #pragma unroll
   for (int t = E / 2; t >= 1; t >>= 1, si++) {
     const bool sol = (SOLMASK >> si) & 1;
 #pragma unroll
     for (int gi = 0; gi < E / (2 * t); gi++) {
       const int p = E / (2 * t) + gi;
-      const u32 ww = UNI ? utw[p] : w[p], wws = UNI ? utws[p] : ws[p];
+      u32 ww, wws;
+      if (UNI) { ww = utw[p]; wws = utws[p]; }
+      else if (STREAM) {
+        if ((p & 3) == 0 || gi == 0) {
+          cw = reinterpret_cast<const uint4 *>(tab)[(p >> 2) * 32 + lane];
+          cws = reinterpret_cast<const uint4 *>(tabs)[(p >> 2) * 32 + lane];
+        }
+        ww = comp4(cw, p & 3); wws = comp4(cws, p & 3);
+      } else { ww = w[p]; wws = ws[p]; }
 #pragma unroll
       for (int j = 0; j < t; j++) {
         const int a = gi * 2 * t + j, b = a + t;
@@ -150,19 +166,29 @@ __device__ __forceinline__ void ct_pass(u32 (&x)[E], const u32 *__restrict__ utw
 // Gentleman-Sande (inverse, unscaled).  B = bound of the inputs in units of Q (<= 16).  Sums double
 // per stage; when they would pass 32Q (= just under 2^32) they are pulled back below 2Q with one
 // lazy Barrett step.  Differences go through the Shoup multiply, which accepts any 32-bit input.
-template <int E, int T, int B, bool UNI, int MAXLAST, int SOLMASK = 0, int SI = 0> struct GsRun {
+template <int E, int T, int B, bool UNI, int MAXLAST, int SOLMASK = 0, int SI = 0, bool STREAM = false> struct GsRun {
   static constexpr int NB = 2 * B;
   static constexpr bool LAST = (2 * T >= E);
   static constexpr bool RED = LAST ? (NB > MAXLAST) : (NB > 16); // pull the sums back below 2Q after this stage?
   static constexpr int OUTB = RED ? 2 : NB;
   __device__ __forceinline__ static void run(u32 (&x)[E], const u32 *__restrict__ utw, const u32 *__restrict__ utws,
-                                             const u32 (&w)[E], const u32 (&ws)[E], u32 Q, u32 mu) {
+                                             const u32 (&w)[E], const u32 (&ws)[E], u32 Q, u32 mu, const u32 *tab = nullptr,
+                                             const u32 *tabs = nullptr, int lane = 0) {
     static_assert(B <= 16, "GS input bound too large");
     const u32 off = B * Q;
+    uint4 cw = make_uint4(0, 0, 0, 0), cws = cw;
 #pragma unroll
     for (int gi = 0; gi < E / (2 * T); gi++) {
       const int p = E / (2 * T) + gi;
-      const u32 ww = UNI ? utw[p] : w[p], wws = UNI ? utws[p] : ws[p];
+      u32 ww, wws;
+      if (UNI) { ww = utw[p]; wws = utws[p]; }
+      else if (STREAM) {
+        if ((p & 3) == 0 || gi == 0) {
+          cw = reinterpret_cast<const uint4 *>(tab)[(p >> 2) * 32 + lane];
+          cws = reinterpret_cast<const uint4 *>(tabs)[(p >> 2) * 32 + lane];
+        }
+        ww = comp4(cw, p & 3); wws = comp4(cws, p & 3);
+      } else { ww = w[p]; wws = ws[p]; }
 #pragma unroll
       for (int j = 0; j < T; j++) {
         const int a = gi * 2 * T + j, b = a + T;
@@ -172,7 +198,7 @@ template <int E, int T, int B, bool UNI, int MAXLAST, int SOLMASK = 0, int SI = 
         x[a] = RED ? lazy_reduce(S, Q, mu) : S;
       }
     }
-    if constexpr (!LAST) GsRun<E, 2 * T, OUTB, UNI, MAXLAST, SOLMASK, SI + 1>::run(x, utw, utws, w, ws, Q, mu);
+    if constexpr (!LAST) GsRun<E, 2 * T, OUTB, UNI, MAXLAST, SOLMASK, SI + 1, STREAM>::run(x, utw, utws, w, ws, Q, mu, tab, tabs, lane);
   }
 };
 // bound (in units of Q) of the values GsRun<E,1,B0,*,MAXLAST> leaves behind
@@ -214,9 +240,13 @@ __device__ __forceinline__ void ntt_forward(u32 (&x)[(1 << LOGN) / 32], u32 *buf
   col_store<E>(buf, x, lane);
   __syncwarp();
   row_load<E>(buf, x, lane);
-  load_lane_tw<E>(tt.fw, w, lane);
-  load_lane_tw<E>(tt.fws, ws, lane);
-  ct_pass<E, false, SOLN>(x, P.tw, P.tws, w, ws, Q, Q2);
+  if constexpr (BFHE_STREAM_TW) {
+    ct_pass<E, false, SOLN, true>(x, P.tw, P.tws, w, ws, Q, Q2, tt.fw, tt.fws, lane);
+  } else {
+    load_lane_tw<E>(tt.fw, w, lane);
+    load_lane_tw<E>(tt.fws, ws, lane);
+    ct_pass<E, false, SOLN>(x, P.tw, P.tws, w, ws, Q, Q2);
+  }
 }
 
 // inverse (unscaled: N * true value; the keys carry N^-1): x in row layout (evaluation form, values < B0*Q)
@@ -226,10 +256,14 @@ __device__ __forceinline__ void ntt_inverse(u32 (&x)[(1 << LOGN) / 32], u32 *buf
   constexpr int E = (1 << LOGN) / 32;
   const u32 Q = P.Q, mu = P.mu;
   u32 w[E], ws[E];
-  load_lane_tw<E>(tt.iw, w, lane);
-  load_lane_tw<E>(tt.iws, ws, lane);
   constexpr int ML = (LOGN & 1) ? 8 : 16; // what the next stage can take
-  GsRun<E, 1, B0, false, ML, SOLN>::run(x, P.itw, P.itws, w, ws, Q, mu);
+  if constexpr (BFHE_STREAM_TW) {
+    GsRun<E, 1, B0, false, ML, SOLN, 0, true>::run(x, P.itw, P.itws, w, ws, Q, mu, tt.iw, tt.iws, lane);
+  } else {
+    load_lane_tw<E>(tt.iw, w, lane);
+    load_lane_tw<E>(tt.iws, ws, lane);
+    GsRun<E, 1, B0, false, ML, SOLN>::run(x, P.itw, P.itws, w, ws, Q, mu);
+  }
   constexpr int B1 = gs_out_bound(E, B0, ML);
   __syncwarp();
   row_store<E>(buf, x, lane);
@@ -352,7 +386,8 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
   u32 *mybuf = dct + ((size_t)g * ROWS + c) * N; // R[g][c] aliases dct row c of gate g
 
   // MAC work split: item -> (chunk qc, gate split)
-  constexpr int GS = (W >= C) ? (W / C) : 1;
+  constexpr bool LEAN = (G > 4); // 3 warps per scheduler: fit 168 registers (no digit array, one output component of keys at a time)
+  constexpr int GS = LEAN ? G / 2 : ((W >= C) ? (W / C) : 1);
   const u32 eA = 2 * brev(lane, 5) + 1; // lane part of the evaluation-point exponent 2*br(idx)+1
 
   for (int step = 0; step < nsteps; step++) {
@@ -372,15 +407,18 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
       // position turns the balanced digits into the plain base-B digits of d + OFF, so digit l is one shift, one mask and
       // one subtraction with no dependency on the digits below it (the top digit wraps exactly like the reference's
       // sign-truncation when dG digits do not cover the centred range, e.g. TOY).
-      u32 dp[E];
+      u32 dp[LEAN ? 1 : E];
+      if constexpr (!LEAN) {
 #pragma unroll
-      for (int k = 0; k < E; k++) dp[k] = ((acc[k] < (Q >> 1)) ? acc[k] : acc[k] - Q) + DIGIT_OFF;
+        for (int k = 0; k < E; k++) dp[k] = ((acc[k] < (Q >> 1)) ? acc[k] : acc[k] - Q) + DIGIT_OFF;
+      }
 #pragma unroll
       for (int l = 0; l < DG; l++) {
         u32 x[E];
 #pragma unroll
         for (int k = 0; k < E; k++) {
-          const u32 r = ((dp[k] >> (LOGBG * l)) & ((1u << LOGBG) - 1)) - (1u << (LOGBG - 1));
+          const u32 dpk = LEAN ? (((acc[k] < (Q >> 1)) ? acc[k] : acc[k] - Q) + DIGIT_OFF) : dp[LEAN ? 0 : k];
+          const u32 r = ((dpk >> (LOGBG * l)) & ((1u << LOGBG) - 1)) - (1u << (LOGBG - 1));
           x[k] = min(r, r + Q);
         }
         u32 *buf = dct + ((size_t)g * ROWS + c + 2 * l) * N;
@@ -391,7 +429,7 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
     pending = pending || active;
     // GINX: this warp's first key chunk is requested BEFORE the barrier, so the L2 round trip overlaps the wait for
     // the slower warps of the CTA instead of stalling the external product (ncu r1: 6 % of samples sat on these loads)
-    uint4 kr[AP ? 1 : 2][ROWS][2];
+    uint4 kr[AP ? 1 : 2][ROWS][LEAN ? 1 : 2];
     if (!AP && warp < C * GS) {
       const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + ((warp % C) * 32 + lane) * 4;
 #pragma unroll
@@ -399,12 +437,70 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
 #pragma unroll
         for (int r = 0; r < ROWS; r++)
 #pragma unroll
-          for (int cc = 0; cc < 2; cc++)
+          for (int cc = 0; cc < (LEAN ? 1 : 2); cc++)
             kr[s][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((s * ROWS + r) * 2 + cc) * N));
     }
     __syncthreads();
 
     // ================= phase B: external product, slot-parallel over the CTA =================
+    if constexpr (LEAN) {
+      // register-lean form: keys of ONE output component (2 signs x ROWS uint4 = 64 registers) at a time, reused by
+      // the gates of this item's group; component-0 results wait in registers until component 1 has read the rows
+      for (int item = warp; item < C * GS; item += W) {
+        const int qc = item % C, gs0 = item / C;
+        u32 eB[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) eB[r] = 2 * ((brev(r, 2) << (LOGN - 2)) | (brev(qc, LOGN - 7) << 5));
+        u32 out0[G / GS][4];
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          if (item != warp || cc == 1) {
+            const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + (qc * 32 + lane) * 4;
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+#pragma unroll
+              for (int r = 0; r < ROWS; r++) kr[s][r][0] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((s * ROWS + r) * 2 + cc) * N));
+          }
+#pragma unroll
+          for (int gl = 0; gl < G / GS; gl++) {
+            const int gg = gs0 + gl * GS;
+            if (gg >= gcount) continue;
+            u32 fp[4], fn[4];
+            const u32 m = s_idx[gg * NPAD + step], mask = 2 * N - 1;
+            const u32 ia = (m * eA) & mask;
+            const u32 A = s_psiM[ia], Ai = s_psiM[(2 * N - ia) & mask];
+            const u32 om = Q - P.oneM;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+              const u32 ib = (m * eB[r]) & mask;
+              const u32 Bv = s_psiM[ib], Bi = s_psiM[(2 * N - ib) & mask];
+              fp[r] = redc((u64)A * Bv, Q, P.qinv_neg) + om;
+              fn[r] = redc((u64)Ai * Bi, Q, P.qinv_neg) + om;
+            }
+            u32 *gd = dct + (size_t)gg * ROWS * N + Lay<E>::chunk_off(lane, qc);
+            u64 sp[4] = {0, 0, 0, 0}, sn[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+              const uint4 dv = *reinterpret_cast<const uint4 *>(gd + (size_t)r * N);
+              const uint4 kp = kr[0][r][0], kn = kr[1][r][0];
+              sp[0] += (u64)dv.x * kp.x; sp[1] += (u64)dv.y * kp.y; sp[2] += (u64)dv.z * kp.z; sp[3] += (u64)dv.w * kp.w;
+              sn[0] += (u64)dv.x * kn.x; sn[1] += (u64)dv.y * kn.y; sn[2] += (u64)dv.z * kn.z; sn[3] += (u64)dv.w * kn.w;
+            }
+            u32 out[4];
+#pragma unroll
+            for (int sl = 0; sl < 4; sl++)
+              out[sl] = redc((u64)redc(sp[sl], Q, P.qinv_neg) * fp[sl] + (u64)redc(sn[sl], Q, P.qinv_neg) * fn[sl], Q, P.qinv_neg);
+            if (cc == 0) {
+#pragma unroll
+              for (int sl = 0; sl < 4; sl++) out0[gl][sl] = out[sl];
+            } else {
+              *reinterpret_cast<uint4 *>(gd) = make_uint4(out0[gl][0], out0[gl][1], out0[gl][2], out0[gl][3]);
+              *reinterpret_cast<uint4 *>(gd + (size_t)N) = make_uint4(out[0], out[1], out[2], out[3]);
+            }
+          }
+        }
+      }
+    } else {
     for (int item = warp; item < C * GS; item += W) {
       const int qc = item % C, gs0 = item / C;
       if (!AP && item != warp) { // further chunks of this warp (fewer warps than chunks)
@@ -478,6 +574,7 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
           *reinterpret_cast<uint4 *>(gd + (size_t)cc * N) = make_uint4(out[0], out[1], out[2], out[3]);
         }
       }
+    }
     }
     __syncthreads();
   }
@@ -922,10 +1019,7 @@ static int launch_br_g(int G, const DevConst &P, const DevGate *d_gates, int cou
   switch (G) {
   case 1: return launch_br_inst<LOGN, DG, LOGBG, 1, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
   case 2: return launch_br_inst<LOGN, DG, LOGBG, 2, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
-  case 5:
-    if constexpr (LOGN == 10 && !AP) return launch_br_inst<LOGN, DG, LOGBG, 5, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
-  case 6:
-    if constexpr (LOGN == 10 && !AP) return launch_br_inst<LOGN, DG, LOGBG, 6, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
+  // (6 gates per CTA -- 3 warps per scheduler through the register-lean LEAN path -- measured 7 % slower than 4: not instantiated)
   default: return launch_br_inst<LOGN, DG, LOGBG, 4, AP>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc, st, info);
   }
 }
