@@ -1050,9 +1050,12 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // narrow wavefront (fewer than 4 gates per SM): the latency variant -- one gate per CTA, one warp per digit row;
-  // wide wavefront: the throughput variant -- G gates per CTA share every bootstrapping-key word
-  const bool lat = force_g == 8 || (force_g == 0 && count <= sms + sms / 2);
+  // Which variant?  latency form: one gate per CTA, one wave of `sms` gates takes ~2.3 ms (STD128_OPT GINX);
+  // throughput form: 4 gates per CTA share every key word, one wave of 4*sms gates takes ~7.6 ms.  Pick the cheaper
+  // estimate (measured on B200, profiles/r1_*): narrow circuit levels go to the latency form, wide batches to the other.
+  const long lat_cost = (long)((count + sms - 1) / sms) * 23;
+  const long thr_cost = (long)((count + 4 * sms - 1) / (4 * sms)) * 76;
+  const bool lat = force_g == 8 || (force_g == 0 && lat_cost <= thr_cost);
   if (lat) {
     if (P.N == 1024 && P.dG == 4 && P.logBG == 7)
       return method_ap ? launch_lat_inst<10, 4, 7, true>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
@@ -1062,7 +1065,7 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
                        : launch_lat_inst<9, 3, 9, false>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);
     return (int)cudaErrorInvalidValue;
   }
-  int G = force_g > 0 ? force_g : (count <= 2 * sms ? 2 : 4);
+  int G = force_g > 0 ? force_g : 4;
   if (P.N == 1024 && P.dG == 4 && P.logBG == 7) {
     return method_ap ? launch_br_g<10, 4, 7, true>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
                      : launch_br_g<10, 4, 7, false>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);

@@ -13,7 +13,7 @@ for count in (1, 148):
     slab = ctx.slab(3 * count); slab.upload(ctx.encrypt(bits, seed=1))
     g = np.zeros(count, dtype=B.GATE_DTYPE)
     g["op"] = B.NAND; g["in0"] = 2 * np.arange(count); g["in1"] = 2 * np.arange(count) + 1; g["out"] = 2 * count + np.arange(count)
-    ctx.dbg_set_gates_per_cta(8)
+    ctx.dbg_set_gates_per_cta(int(os.environ.get('GPC', '8')))
     acc = ctx.dbg_blind_rotate(slab, g)
     t = acc[:, :, 32:37].astype(np.float64)  # kilo-cycles per phase, warps 0 and 1
     names = ["intt+decompose", "barrier1", "ntt", "barrier2+keywait", "mac"]
