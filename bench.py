@@ -269,7 +269,9 @@ def main():
                 "work_per_unit": "%d IMAD-class instr per bootstrapped gate (3 x 45.25M modular multiplications, SURVEY 8(d))" % W_IMAD,
                 "kernel_ms_per_launch": 1e3 * br_s_per_launch, "kernel_share_of_step": br_ms / (br_ms + ks_ms + nt_ms),
                 "step_ms_by_kernel": {"blind_rotate": br_ms / args.steps, "keyswitch": ks_ms / args.steps, "eval_not": nt_ms / args.steps},
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on a 592-gate
+                # launch (profiles/r1_blind_rotate_ncu_summary.md): the 65.8 MB key is read from HBM once, then served by L2
+                "traffic": 73.1e6, "traffic_note": "bytes per 592-gate launch (ncu); algorithmic key bytes reach DRAM once per launch",
                 "hbm": {"achieved": boots_per_launch * hbm_bytes_per_boot / br_s_per_launch / 1e9, "peak": peak_hbm(),
                         "unit": "GB/s", "bytes_per_unit": hbm_bytes_per_boot,
                         "note": "key streaming is L2/HBM traffic shared by the %d gates of a CTA tile; the path is integer-bound" % tile}}
