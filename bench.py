@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--gates", type=int, default=24576, help="gates per rank per step (config 3 mix)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-aux", action="store_true", help="skip the AES-128 circuit wall-time figure")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="gates in the CPU baseline sample (0 = 4 per core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="gates in the CPU baseline sample (0 = 16 per core; reference arm: 8 per core per step)")
     return ap.parse_args()
 
 
@@ -138,7 +138,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or 2 * cores
+    sample = args.cpu_sample or 8 * cores  # ~0.7 s per step on 16 cores; XOR gates are 3 serial bootstraps inside one task
     o, g, slab, boots, cores, bits = cpu_baseline(sample)
     times = []
     for it in range(args.warmup + args.steps):
@@ -292,7 +292,7 @@ def main():
             "roofline": roofline, "clocks": clocks}
     if rank == 0 and world == 1:
         cores = os.cpu_count() or 1
-        sample = args.cpu_sample or 4 * cores
+        sample = args.cpu_sample or 16 * cores  # about 20-30 core-seconds of CPU work
         o, g, s2, b2, cores, _ = cpu_baseline(sample)
         t = time.perf_counter()
         o.eval_gates(g, s2, nthreads=cores)
