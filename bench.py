@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--gates", type=int, default=24576, help="gates per rank per step (config 3 mix)")
+    ap.add_argument("--gates", type=int, default=0,
+                    help="gates per rank per step (config 3 mix); 0 = 42 full waves of 4-gate CTAs (24 864 on a 148-SM B200)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-aux", action="store_true", help="skip the AES-128 circuit wall-time figure")
     ap.add_argument("--cpu-sample", type=int, default=0, help="gates in the CPU baseline sample (0 = 16 per core; reference arm: 8 per core per step)")
@@ -201,7 +202,9 @@ def main():
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
-    count = args.gates
+    # default batch: a multiple of 3 (gate mix) x 4 (gates per CTA) x SM count, so every launch is whole waves
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    count = args.gates or 3 * 4 * sms * 14
     n_in = 2 * count
     gates, boots = make_workload(B, count, n_in)
     bits = np.random.default_rng(42 + rank).integers(0, 2, n_in)

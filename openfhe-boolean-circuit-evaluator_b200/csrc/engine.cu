@@ -140,10 +140,21 @@ extern "C" bfhe_ctx *bfhe_create(int paramset, int method, int device) {
               cudaMemcpy(c->d_psiM, psiM.data(), psiM.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc(&c->d_gates, bfhe_ctx::CHUNK * sizeof(DevGate)) == cudaSuccess &&
               cudaMalloc(&c->d_ext, bfhe_ctx::CHUNK * (size_t)(N + 4) * 4) == cudaSuccess &&
+              cudaMalloc(&c->d_gates_b, bfhe_ctx::CHUNK * sizeof(DevGate)) == cudaSuccess &&
+              cudaMalloc(&c->d_ext_b, bfhe_ctx::CHUNK * (size_t)(N + 4) * 4) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->ks_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_br[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_br[1], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_ks[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_ks[1], cudaEventDisableTiming) == cudaSuccess &&
               cudaMallocHost(&c->h_gates[0], bfhe_ctx::CHUNK * sizeof(DevGate)) == cudaSuccess &&
               cudaMallocHost(&c->h_gates[1], bfhe_ctx::CHUNK * sizeof(DevGate)) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->stage_ev[0], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->stage_ev[1], cudaEventDisableTiming) == cudaSuccess;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    c->chunk = std::max<size_t>(1, bfhe_ctx::CHUNK / (4 * (size_t)sms)) * 4 * (size_t)sms; // whole waves of 4-gate CTAs
+    if (c->chunk > bfhe_ctx::CHUNK) c->chunk = bfhe_ctx::CHUNK;
     if (!ok) {
       cuda_fail(cudaGetLastError(), "bfhe_create: device allocation");
       bfhe_destroy(c);
@@ -161,6 +172,12 @@ extern "C" void bfhe_destroy(bfhe_ctx *c) {
     for (auto &s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     cudaFree(c->d_bk); cudaFree(c->d_twl); cudaFree(c->d_psiM); cudaFree(c->d_ksk); cudaFree(c->d_gates); cudaFree(c->d_ext);
     cudaFree(c->d_tmp); cudaFree(c->d_ptr_in); cudaFree(c->d_ptr_out); cudaFree(c->e2e_slab);
+    cudaFree(c->d_gates_b); cudaFree(c->d_ext_b);
+    for (int i = 0; i < 2; i++) {
+      if (c->ev_br[i]) cudaEventDestroy(c->ev_br[i]);
+      if (c->ev_ks[i]) cudaEventDestroy(c->ev_ks[i]);
+    }
+    if (c->ks_stream) cudaStreamDestroy(c->ks_stream);
     for (int i = 0; i < 2; i++) {
       if (c->h_gates[i]) cudaFreeHost(c->h_gates[i]);
       if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
@@ -503,45 +520,63 @@ extern "C" int bfhe_slab_download(bfhe_ctx *c, const uint32_t *slab, size_t firs
 // -------------------------------------------------------------------------------------------------
 // hot path
 // -------------------------------------------------------------------------------------------------
-static void prof_begin(bfhe_ctx *c, int kernel) {
+static void prof_begin(bfhe_ctx *c, int kernel, cudaStream_t st = nullptr) {
   if (!c->profiling) return;
   ProfSpan s;
   s.kernel = kernel;
   cudaEventCreate(&s.a);
   cudaEventCreate(&s.b);
-  cudaEventRecord(s.a, c->stream);
+  cudaEventRecord(s.a, st ? st : c->stream);
   c->spans.push_back(s);
 }
-static void prof_end(bfhe_ctx *c) {
+static void prof_end(bfhe_ctx *c, cudaStream_t st = nullptr) {
   if (!c->profiling) return;
-  cudaEventRecord(c->spans.back().b, c->stream);
+  cudaEventRecord(c->spans.back().b, st ? st : c->stream);
 }
 
 int bfhe::run_gate_list(bfhe_ctx *c, const DevGate *list, size_t count, u32 *acc_dbg_host) {
   const u32 N = c->p.N;
   u32 *d_acc = nullptr;
-  if (acc_dbg_host) BFHE_CUDA(cudaMalloc(&d_acc, std::min(count, bfhe_ctx::CHUNK) * 2 * N * 4));
-  for (size_t off = 0; off < count; off += bfhe_ctx::CHUNK) {
-    const size_t m = std::min(bfhe_ctx::CHUNK, count - off);
+  if (acc_dbg_host) BFHE_CUDA(cudaMalloc(&d_acc, std::min(count, c->chunk) * 2 * N * 4));
+  // Gates of one list are independent, so with several chunks the (HBM-bound) key switch of chunk k runs on a side
+  // stream underneath the (integer-bound) blind rotation of chunk k+1; two sets of descriptor / ext buffers.
+  const bool overlap = count > c->chunk && !acc_dbg_host;
+  int k = 0;
+  for (size_t off = 0; off < count; off += c->chunk, k++) {
+    const size_t m = std::min(c->chunk, count - off);
+    const int b = overlap ? (k & 1) : 0;
+    DevGate *dg = b ? c->d_gates_b : c->d_gates;
+    u32 *de = b ? c->d_ext_b : c->d_ext;
+    if (overlap && k >= 2) BFHE_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ks[b], 0)); // buffers of chunk k-2 are free again
     const int sb = c->stage_next;
     c->stage_next ^= 1;
     BFHE_CUDA(cudaEventSynchronize(c->stage_ev[sb])); // staging buffer free again?
     std::memcpy(c->h_gates[sb], list + off, m * sizeof(DevGate));
-    BFHE_CUDA(cudaMemcpyAsync(c->d_gates, c->h_gates[sb], m * sizeof(DevGate), cudaMemcpyHostToDevice, c->stream));
+    BFHE_CUDA(cudaMemcpyAsync(dg, c->h_gates[sb], m * sizeof(DevGate), cudaMemcpyHostToDevice, c->stream));
     BFHE_CUDA(cudaEventRecord(c->stage_ev[sb], c->stream));
     prof_begin(c, 0);
-    int rc = launch_blind_rotate(c->P, c->p.method == BFHE_AP, c->d_gates, (int)m, c->d_bk, c->d_twl, c->d_psiM, c->d_ext, d_acc,
-                                 c->force_g, c->stream, nullptr);
+    int rc = launch_blind_rotate(c->P, c->p.method == BFHE_AP, dg, (int)m, c->d_bk, c->d_twl, c->d_psiM, de, d_acc, c->force_g,
+                                 c->stream, nullptr);
     prof_end(c);
     if (rc) return cuda_fail((cudaError_t)rc, "blind_rotate launch");
     if (acc_dbg_host) {
       BFHE_CUDA(cudaMemcpyAsync(acc_dbg_host + off * 2 * N, d_acc, m * 2 * N * 4, cudaMemcpyDeviceToHost, c->stream));
       BFHE_CUDA(cudaStreamSynchronize(c->stream));
     }
-    prof_begin(c, 1);
-    rc = launch_keyswitch(c->P, c->d_ext, c->d_gates, (int)m, c->d_ksk, c->ksk_elem_bytes, c->stream);
-    prof_end(c);
+    cudaStream_t kst = overlap ? c->ks_stream : c->stream;
+    if (overlap) {
+      BFHE_CUDA(cudaEventRecord(c->ev_br[b], c->stream));
+      BFHE_CUDA(cudaStreamWaitEvent(c->ks_stream, c->ev_br[b], 0));
+    }
+    prof_begin(c, 1, kst);
+    rc = launch_keyswitch(c->P, de, dg, (int)m, c->d_ksk, c->ksk_elem_bytes, kst);
+    prof_end(c, kst);
     if (rc) return cuda_fail((cudaError_t)rc, "keyswitch launch");
+    if (overlap) BFHE_CUDA(cudaEventRecord(c->ev_ks[b], c->ks_stream));
+  }
+  if (overlap) { // the caller's stream sees every output before anything it enqueues next
+    BFHE_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ks[0], 0));
+    if (k >= 2) BFHE_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ks[1], 0));
   }
   if (d_acc) { cudaStreamSynchronize(c->stream); cudaFree(d_acc); }
   return BFHE_OK;

@@ -48,8 +48,13 @@ struct bfhe_ctx {
   bool dev_keys = false;
 
   // per-call scratch
-  static constexpr size_t CHUNK = 32768; // gates per blind-rotation launch
-  bfhe::DevGate *d_gates = nullptr;      // CHUNK entries
+  static constexpr size_t CHUNK = 32768; // upper bound of gates per blind-rotation launch (buffer sizes)
+  size_t chunk = CHUNK;                  // actual launch size: largest multiple of one full wave (4 gates x SM count) <= CHUNK
+  bfhe::DevGate *d_gates = nullptr;      // CHUNK entries (buffer 0)
+  bfhe::DevGate *d_gates_b = nullptr;    // buffer 1: key switch of chunk k overlaps blind rotation of chunk k+1
+  bfhe::u32 *d_ext_b = nullptr;
+  cudaStream_t ks_stream = nullptr;
+  cudaEvent_t ev_br[2] = {nullptr, nullptr}, ev_ks[2] = {nullptr, nullptr};
   bfhe::DevGate *h_gates[2] = {nullptr, nullptr}; // pinned staging
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   int stage_next = 0;
