@@ -151,6 +151,22 @@ extern "C" bfhe_ctx *bfhe_create(int paramset, int method, int device) {
               cudaMallocHost(&c->h_gates[1], bfhe_ctx::CHUNK * sizeof(DevGate)) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->stage_ev[0], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->stage_ev[1], cudaEventDisableTiming) == cudaSuccess;
+    if (ok && v2_supported(P, method == BFHE_AP)) { // tables of the second-generation throughput kernel
+      std::vector<u32> t2(4 * (size_t)N), F(2 * (size_t)N);
+      for (u32 k = 0; k < N; k++) { // natural order, last stage de-interleaved (kernels_v2.cu load_tw_narrow)
+        u32 d = k;
+        if (k >= N / 2) { const u32 i = k - N / 2, t = i >> 3, j = i & 7; d = N / 2 + (N / 4) * (j >> 2) + 4 * t + (j & 3); }
+        t2[d] = c->hntt.tw[k]; t2[N + d] = shoup32(c->hntt.tw[k], Q);
+        t2[2 * N + d] = c->hntt.itw[k]; t2[3 * N + d] = shoup32(c->hntt.itw[k], Q);
+      }
+      const u64 oneM = (1ull << 32) % Q;
+      for (u32 k = 0; k < 2 * N; k++) // (psi^k - 1) in Montgomery form, stored at the 11-bit rotation of k (kernels_v2.cu f_index)
+        F[((k >> 5) & 63u) | ((k & 31u) << 6)] = (u32)((psiM[k] + Q - oneM) % Q);
+      ok = cudaMalloc(&c->d_tw2, t2.size() * 4) == cudaSuccess && cudaMalloc(&c->d_F, F.size() * 4) == cudaSuccess &&
+           cudaMemcpy(c->d_tw2, t2.data(), t2.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+           cudaMemcpy(c->d_F, F.data(), F.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+      c->v2.d_tw2 = c->d_tw2; c->v2.d_F = c->d_F;
+    }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     c->chunk = std::max<size_t>(1, bfhe_ctx::CHUNK / (4 * (size_t)sms)) * 4 * (size_t)sms; // whole waves of 4-gate CTAs
@@ -173,6 +189,7 @@ extern "C" void bfhe_destroy(bfhe_ctx *c) {
     cudaFree(c->d_bk); cudaFree(c->d_twl); cudaFree(c->d_psiM); cudaFree(c->d_ksk); cudaFree(c->d_gates); cudaFree(c->d_ext);
     cudaFree(c->d_tmp); cudaFree(c->d_ptr_in); cudaFree(c->d_ptr_out); cudaFree(c->e2e_slab);
     cudaFree(c->d_gates_b); cudaFree(c->d_ext_b);
+    cudaFree(c->d_bk2); cudaFree(c->d_tw2); cudaFree(c->d_F);
     for (int i = 0; i < 2; i++) {
       if (c->ev_br[i]) cudaEventDestroy(c->ev_br[i]);
       if (c->ev_ks[i]) cudaEventDestroy(c->ev_ks[i]);
@@ -337,6 +354,14 @@ int bfhe::ensure_device_keys(bfhe_ctx *c) {
       BFHE_CUDA(cudaStreamSynchronize(c->stream));
     }
     cudaFree(d_coef);
+  }
+  cudaFree(c->d_bk2); c->d_bk2 = nullptr; c->v2.d_bk2 = nullptr;
+  if (c->d_tw2 && v2_supported(c->P, p.method == BFHE_AP)) { // second copy in the physical slot order of kernels_v2.cu
+    BFHE_CUDA(cudaMalloc(&c->d_bk2, c->bk_words * 4));
+    int rc = launch_bk_permute_v2(c->d_bk, c->d_bk2, c->bk_words / N, c->stream);
+    if (rc) return cuda_fail((cudaError_t)rc, "bk_permute_v2");
+    BFHE_CUDA(cudaStreamSynchronize(c->stream));
+    c->v2.d_bk2 = c->d_bk2;
   }
   { // KSK: [i][j(digit value)][k(digit index)][n+1]  ->  [i][k][j][rowlen]
     const u32 rowlen = c->ksk_elem_bytes == 2 ? 512 : p.ct_stride; // elements per padded row
@@ -556,7 +581,7 @@ int bfhe::run_gate_list(bfhe_ctx *c, const DevGate *list, size_t count, u32 *acc
     BFHE_CUDA(cudaEventRecord(c->stage_ev[sb], c->stream));
     prof_begin(c, 0);
     int rc = launch_blind_rotate(c->P, c->p.method == BFHE_AP, dg, (int)m, c->d_bk, c->d_twl, c->d_psiM, de, d_acc, c->force_g,
-                                 c->stream, nullptr);
+                                 c->stream, nullptr, &c->v2);
     prof_end(c);
     if (rc) return cuda_fail((cudaError_t)rc, "blind_rotate launch");
     if (acc_dbg_host) {

@@ -1,0 +1,472 @@
+// kernels_v2.cu -- second-generation throughput kernel for the GINX blind rotation (STD128_OPT shape: N = 1024, dG = 4,
+// Bg = 2^7).  Same arithmetic as blind_rotate_kernel in kernels.cu (the reference reaches it
+// through BinFHEContext::EvalBinGate, src/gate.cpp:133,172,200-202 in /root/reference), different mapping to the SM:
+//
+//  * 16 warps per CTA instead of 8 (<= 128 registers per thread): every transform works on 16-value register tiles
+//    (three passes 4 + 3 + 3 stages with two in-place shared-memory transposes) instead of 32-value tiles.  Four warps
+//    per scheduler hide the fixed IMAD / IMAD.HI latencies that left the FMA-heavy pipe 27 % idle with two.
+//  * A CTA still carries 4 gates, but as two independent PAIRS of gates (8 warps each) that only meet at named
+//    barriers of their own pair: one pair's external product overlaps the other pair's transforms.
+//  * Per gate and accumulator component two warps: the inverse transform is split across them (64-thread named
+//    barrier), then each runs two of the four digit transforms on its own.
+//  * The accumulator lives in shared memory in "centred + digit offset" form (what the digit extraction consumes).
+//  * One shared-memory layout (phys()) serves all three register-tile shapes conflict-free: 32-bit column access,
+//    64-bit pair access, 128-bit row access (checked by tools/smem_layout_check.py).
+//  * MAC_FP64 = true computes the external product on the FP64 pipe (exact integer arithmetic in doubles: key words
+//    split 14 + 13 bits so every partial sum stays below 2^53), which runs concurrently with the integer pipes
+//    (tools/pipe_probe.cu: IMAD + DFMA pairs issue at the rate of either alone).
+#include "common.hpp"
+#include <cuda_runtime.h>
+
+namespace bfhe {
+namespace v2 {
+
+constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, G = 4, NPAD = 512, THREADS = 512;
+constexpr u32 DIGIT_OFF = 64u + (64u << 7) + (64u << 14) + (64u << 21);
+constexpr u32 SOLINAS_Q = (1u << 27) - (1u << 11) + 1;
+
+__device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q) { return x * w - __umulhi(x, ws) * Q; } // [0,2Q)
+__device__ __forceinline__ u32 redc(u64 s, u32 Q, u32 qinv_neg) { // s * 2^-32 mod Q, lazy
+  const u32 m = (u32)s * qinv_neg;
+  return (u32)((s + (u64)m * Q) >> 32);
+}
+__device__ __forceinline__ u32 lazy_reduce(u32 x, u32 Q) { return x - (x >> 27) * Q; } // floor(2^32/Q) = 32: any x -> [0,2Q)
+__device__ __forceinline__ u32 csub(u32 x, u32 Q) { return min(x, x - Q); }
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// position p of a polynomial (coefficient index going in, bit-reversed evaluation slot coming out) -> word offset in its
+// shared-memory row.  Rows of 16 words; 16-byte chunks XOR-swizzled by the row number; row pairs swapped by bit 3 of the row.
+__host__ __device__ __forceinline__ int phys(int p) {
+  const int T3 = p >> 4, c = (p >> 2) & 3;
+  return 16 * (T3 ^ ((T3 >> 3) & 1)) + 4 * (c ^ ((T3 >> 1) & 3)) + (p & 3);
+}
+__host__ __device__ __forceinline__ int unphys(int o) {
+  const int rho = o >> 4, T3 = rho ^ ((rho >> 3) & 1);
+  return 16 * T3 + 4 * (((o >> 2) & 3) ^ ((T3 >> 1) & 3)) + (o & 3);
+}
+
+// ---- butterfly stages on a 16-register tile -------------------------------------------------------------------------
+// Cooley-Tukey, half-sizes TBEG, TBEG/2, ..., TEND; group gi of the stage with half-size t uses twiddle w[16/(2t) + gi].
+// No range correction: values grow by 2Q per stage (21Q < 2^32 after all ten).
+template <int TBEG, int TEND>
+__device__ __forceinline__ void ct_stages(u32 (&x)[16], const u32 *__restrict__ w, const u32 *__restrict__ ws, u32 Q, u32 Q2) {
+#pragma unroll
+  for (int t = TBEG; t >= TEND; t >>= 1) {
+#pragma unroll
+    for (int gi = 0; gi < 16 / (2 * t); gi++) {
+      const int p = 16 / (2 * t) + gi;
+#pragma unroll
+      for (int j = 0; j < t; j++) {
+        const int a = gi * 2 * t + j, b = a + t;
+        const u32 T = mul_shoup(x[b], w[p], ws[p], Q);
+        x[b] = x[a] - T + Q2;
+        x[a] = x[a] + T;
+      }
+    }
+  }
+}
+// Gentleman-Sande, half-sizes T, 2T, ..., TEND.  B = bound of the inputs in units of Q (<= 16).  Sums double per stage and are
+// pulled back below 2Q with one lazy Barrett step when they would pass 32Q; differences go through the Shoup multiply.
+__host__ __device__ constexpr int gs_bound(int T, int TEND, int B, int MAXOUT) {
+  for (; T <= TEND; T *= 2) {
+    const int NB = 2 * B;
+    B = ((T == TEND) ? NB > MAXOUT : NB > 16) ? 2 : NB;
+  }
+  return B;
+}
+template <int T, int TEND, int B, int MAXOUT> struct Gs {
+  static constexpr int NB = 2 * B;
+  static constexpr bool LAST = (T == TEND);
+  static constexpr bool RED = LAST ? (NB > MAXOUT) : (NB > 16);
+  static constexpr int OUTB = RED ? 2 : NB;
+  __device__ __forceinline__ static void run(u32 (&x)[16], const u32 *__restrict__ w, const u32 *__restrict__ ws, u32 Q) {
+    static_assert(B <= 16, "GS input bound too large");
+    const u32 off = B * Q;
+#pragma unroll
+    for (int gi = 0; gi < 16 / (2 * T); gi++) {
+      const int p = 16 / (2 * T) + gi;
+#pragma unroll
+      for (int j = 0; j < T; j++) {
+        const int a = gi * 2 * T + j, b = a + T;
+        const u32 S = x[a] + x[b];
+        const u32 D = x[a] - x[b] + off;
+        x[b] = mul_shoup(D, w[p], ws[p], Q);
+        x[a] = RED ? lazy_reduce(S, Q) : S;
+      }
+    }
+    if constexpr (!LAST) Gs<2 * T, TEND, OUTB, MAXOUT>::run(x, w, ws, Q);
+  }
+};
+
+// host-side index of twiddle (m groups, group i) in the tables: natural order m + i, except the last stage (m = 512), whose
+// groups 8t + j sit at 512 + 256*(j >> 2) + 4t + (j & 3)
+struct Tabs { // shared memory
+  const u32 *fw, *fws, *iw, *iws;
+};
+
+// per-thread twiddles of the middle pass (positions 64u + 8r + 2w + b: stages with 16, 32, 64 groups) and of the narrow
+// pass (positions 16*T3 + j: stages with 128, 256, 512 groups), fetched as 32/64/128-bit loads from the natural-order tables
+__device__ __forceinline__ void load_tw_mid(const u32 *tab, u32 (&w)[16], int u) {
+  w[1] = tab[16 + u];
+  const uint2 a = *reinterpret_cast<const uint2 *>(tab + 32 + 2 * u);
+  w[2] = a.x; w[3] = a.y;
+  const uint4 b = *reinterpret_cast<const uint4 *>(tab + 64 + 4 * u);
+  w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+__device__ __forceinline__ void load_tw_narrow(const u32 *tab, u32 (&w)[16], int T3) {
+  const uint2 a = *reinterpret_cast<const uint2 *>(tab + 128 + 2 * T3);
+  w[2] = a.x; w[3] = a.y;
+  const uint4 b = *reinterpret_cast<const uint4 *>(tab + 256 + 4 * T3);
+  w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  // the 512-group stage is stored de-interleaved (groups 8*T3+0..3 | groups 8*T3+4..7) so both loads are contiguous across lanes
+  const uint4 c = *reinterpret_cast<const uint4 *>(tab + 512 + 4 * T3);
+  const uint4 d = *reinterpret_cast<const uint4 *>(tab + 768 + 4 * T3);
+  w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w; w[12] = d.x; w[13] = d.y; w[14] = d.z; w[15] = d.w;
+}
+// tile I/O in the three shapes (T = logical thread 0..63 of the polynomial).  Every address is one per-thread base XOR a
+// compile-time constant (tools/smem_layout_check.py proves these forms equal phys()).
+__device__ __forceinline__ int col_base(int T) { return 16 * (T >> 4) + 4 * (((T >> 2) & 3) ^ (T >> 5)) + (T & 3); }
+__device__ __forceinline__ int mid_base(int T) {
+  const int u = T >> 2, w = T & 3;
+  return 64 * u + 16 * ((u >> 1) & 1) + 8 * (u & 1) + 4 * (w >> 1) + 2 * (w & 1);
+}
+__device__ __forceinline__ int row_base(int T3) { return 16 * (T3 ^ ((T3 >> 3) & 1)) + 4 * ((T3 >> 1) & 3); }
+__device__ __forceinline__ void col_load(const u32 *buf, u32 (&x)[16], int T) { // positions T + 64k
+  const int b = col_base(T);
+  const u32 *a0 = buf + b, *a1 = buf + (b ^ 8), *a2 = buf + (b ^ 16), *a3 = buf + (b ^ 24);
+#pragma unroll
+  for (int k = 0; k < 16; k++) x[k] = ((k & 3) == 0 ? a0 : (k & 3) == 1 ? a1 : (k & 3) == 2 ? a2 : a3)[64 * k];
+}
+__device__ __forceinline__ void col_store(u32 *buf, const u32 (&x)[16], int T) {
+  const int b = col_base(T);
+  u32 *a0 = buf + b, *a1 = buf + (b ^ 8), *a2 = buf + (b ^ 16), *a3 = buf + (b ^ 24);
+#pragma unroll
+  for (int k = 0; k < 16; k++) ((k & 3) == 0 ? a0 : (k & 3) == 1 ? a1 : (k & 3) == 2 ? a2 : a3)[64 * k] = x[k];
+}
+__device__ __forceinline__ constexpr int mid_k(int r) { return 32 * (r >> 2) + 16 * ((r >> 1) & 1) + 8 * (r & 1) + 4 * (r >> 2); }
+__device__ __forceinline__ void mid_load(const u32 *buf, u32 (&x)[16], int T) { // positions 64u + 8r + 2w + {0,1}, T = 4u + w
+  const int b = mid_base(T);
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const uint2 v = *reinterpret_cast<const uint2 *>(buf + (b ^ mid_k(r)));
+    x[2 * r] = v.x; x[2 * r + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void mid_store(u32 *buf, const u32 (&x)[16], int T) {
+  const int b = mid_base(T);
+#pragma unroll
+  for (int r = 0; r < 8; r++) *reinterpret_cast<uint2 *>(buf + (b ^ mid_k(r))) = make_uint2(x[2 * r], x[2 * r + 1]);
+}
+__device__ __forceinline__ void row_load(const u32 *buf, u32 (&x)[16], int T3) { // positions 16*T3 + j
+  const int b = row_base(T3);
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(buf + (b ^ (4 * c)));
+    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void row_store(u32 *buf, const u32 (&x)[16], int T3) {
+  const int b = row_base(T3);
+#pragma unroll
+  for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(buf + (b ^ (4 * c))) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+}
+
+// forward transform of digit l of the accumulator component published in dp[] (centred + DIGIT_OFF, natural order), by ONE
+// warp (two 16-value tiles per pass); the result (bit-reversed evaluation order, lazy < 21Q) lands in row `buf`.
+__device__ __forceinline__ void ntt_forward_digit(const u32 *dp, int l, u32 *buf, const DevConst &P, const Tabs &tt, int lane) {
+  const u32 Q = P.Q, Q2 = P.Q2;
+#pragma unroll 1
+  for (int it = 0; it < 2; it++) { // wide pass: positions T + 64k, stages with 1, 2, 4, 8 groups (uniform twiddles: constant bank)
+    const int T = 32 * it + lane;
+    u32 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const u32 r = ((dp[T + 64 * k] >> (LOGBG * l)) & ((1u << LOGBG) - 1)) - (1u << (LOGBG - 1));
+      x[k] = min(r, r + Q);
+    }
+    ct_stages<8, 1>(x, P.tw, P.tws, Q, Q2);
+    col_store(buf, x, T);
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int it = 0; it < 2; it++) { // middle pass, in place
+    const int T = 32 * it + lane;
+    u32 x[16], w[16], ws[16];
+    load_tw_mid(tt.fw, w, T >> 2);
+    load_tw_mid(tt.fws, ws, T >> 2);
+    mid_load(buf, x, T);
+    ct_stages<8, 2>(x, w, ws, Q, Q2);
+    mid_store(buf, x, T);
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int it = 0; it < 2; it++) { // narrow pass, in place
+    const int T = 32 * it + lane;
+    u32 x[16], w[16], ws[16];
+    load_tw_narrow(tt.fw, w, T);
+    load_tw_narrow(tt.fws, ws, T);
+    row_load(buf, x, T);
+    ct_stages<4, 1>(x, w, ws, Q, Q2);
+    row_store(buf, x, T);
+  }
+}
+
+// inverse transform (unscaled; the keys carry N^-1) of row `buf` (values < B0*Q) by TWO warps, T = 32*h + lane; on return
+// x[k] = coefficient T + 64k, fully reduced.  bar_id: named barrier of this warp pair.
+template <int B0> __device__ __forceinline__ void ntt_inverse_split(u32 (&x)[16], u32 *buf, const DevConst &P, const Tabs &tt, int T, int bar_id) {
+  const u32 Q = P.Q;
+  {
+    u32 w[16], ws[16];
+    load_tw_narrow(tt.iw, w, T);
+    load_tw_narrow(tt.iws, ws, T);
+    row_load(buf, x, T);
+    Gs<1, 4, B0, 16>::run(x, w, ws, Q);
+    row_store(buf, x, T);
+  }
+  constexpr int B1 = gs_bound(1, 4, B0, 16);
+  bar_sync(bar_id, 64);
+  {
+    u32 w[16], ws[16];
+    load_tw_mid(tt.iw, w, T >> 2);
+    load_tw_mid(tt.iws, ws, T >> 2);
+    mid_load(buf, x, T);
+    Gs<2, 8, B1, 16>::run(x, w, ws, Q);
+    mid_store(buf, x, T);
+  }
+  constexpr int B2 = gs_bound(2, 8, B1, 16);
+  bar_sync(bar_id, 64);
+  col_load(buf, x, T);
+  Gs<1, 8, B2, 32>::run(x, P.itw, P.itws, Q);
+#pragma unroll
+  for (int k = 0; k < 16; k++) x[k] = csub(lazy_reduce(x[k], Q), Q);
+}
+
+// table of (psi^k - 1): the lanes of a warp own slots whose exponents differ in bits 4..8, so entry k is stored at the
+// 11-bit rotation of k by 5 (bank = bits 5..9 of k): 1.5 wavefronts per gather on average instead of 16
+__host__ __device__ __forceinline__ u32 f_index(u32 k) { return ((k >> 5) & 63u) | ((k & 31u) << 6); }
+
+struct Cfg {
+  static constexpr size_t dct_words = (size_t)G * ROWS * N;  // [gate][row][phys]
+  static constexpr size_t dp_words = (size_t)G * 2 * N;      // [gate][component][natural]
+  static constexpr size_t tw_words = 4 * N;                  // fw | fws | iw | iws
+  static constexpr size_t f_words = 2 * N;                   // (psi^k - 1) in Montgomery form
+  static constexpr size_t smem_bytes = (dct_words + dp_words + tw_words + f_words) * 4 + (size_t)G * NPAD * 2;
+};
+
+template <bool MAC_FP64>
+__global__ void __launch_bounds__(THREADS, 1)
+blind_rotate_v2_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count, const u32 *__restrict__ bk,
+                       const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u32 *dct = reinterpret_cast<u32 *>(smem_raw);
+  u32 *dpb = dct + Cfg::dct_words;
+  u32 *s_tw = dpb + Cfg::dp_words;
+  u32 *s_F = s_tw + Cfg::tw_words;
+  u16 *s_idx = reinterpret_cast<u16 *>(s_F + Cfg::f_words);
+  __shared__ u32 s_b[G];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pair = warp >> 3, g = warp >> 2, c = (warp >> 1) & 1, h = warp & 1; // g = gate within the CTA (2*pair + 0/1)
+  const int gate0 = blockIdx.x * G;
+  const int gcount = min(G, count - gate0);
+  const u32 Q = P.Q, q = P.q, n = P.n;
+  const int pair_bar = 1 + pair, poly_bar = 3 + (warp >> 1);
+
+  for (int i = tid; i < 4 * N; i += THREADS) s_tw[i] = g_tw[i];
+  for (int i = tid; i < 2 * N; i += THREADS) s_F[i] = g_F[i];
+  const Tabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
+
+  // ---- prologue: LWE prep (EvalBinGate's ct1+ct2 / 2(ct1-ct2) / Bootstrap's b+q/4, with fused EvalNOT), as in kernels.cu ----
+  for (int gg = 0; gg < gcount; gg++) {
+    const DevGate dg = gates[gate0 + gg];
+    const u32 gate = dg.op & 0xff;
+    for (u32 i = tid; i <= n; i += THREADS) {
+      u32 x = dg.in0[i];
+      if (dg.op & OP_NEG0) x = (i == n) ? (q / 4 + q - x) % q : (q - x) % q;
+      u32 v;
+      if (gate == OP_BOOTSTRAP) {
+        v = (i == n) ? (x + q / 4) % q : x;
+      } else {
+        u32 y = dg.in1[i];
+        if (dg.op & OP_NEG1) y = (i == n) ? (q / 4 + q - y) % q : (q - y) % q;
+        v = (gate == OP_XOR_FAST || gate == OP_XNOR_FAST) ? (2 * (x + q - y)) % q : (x + y) % q;
+      }
+      if (i == n) s_b[gg] = v;
+      else s_idx[gg * NPAD + i] = (u16)(((q - v) % q) * P.factor); // monomial exponent in [0,2N)
+    }
+  }
+  __syncthreads();
+
+  // ---- accumulator init: acc = (0, testvector), published as centred + DIGIT_OFF ----
+  const bool gvalid = g < gcount;
+  const int T = 32 * h + lane; // logical thread of this warp pair's polynomial
+  u32 *mydp = dpb + ((size_t)g * 2 + c) * N;
+  u32 *myrow = dct + ((size_t)g * ROWS + c) * N; // R[g][c] aliases dct row c of gate g
+  if (gvalid) {
+    u32 q1 = 0, q2 = 0, b = 0;
+    if (c == 1) {
+      const u32 gate = gates[gate0 + g].op & 0xff;
+      q1 = P.gate_const[gate == OP_BOOTSTRAP ? OP_AND : gate];
+      q2 = (q1 + q / 2) % q;
+      b = s_b[g];
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const u32 idx = T + 64 * k;
+      u32 v = DIGIT_OFF;
+      if (c == 1 && idx % P.factor == 0) {
+        const u32 t = (b + q - idx / P.factor) % q;
+        const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
+        v = in ? DIGIT_OFF - P.Q8 : DIGIT_OFF + P.Q8; // -(Q/8+1) / +(Q/8+1), centred
+      }
+      mydp[idx] = v;
+    }
+  }
+
+  // ---- external product: thread tp of the pair owns the 4 evaluation slots stored at words 4*tp .. 4*tp+3 of every row ----
+  const int tp = tid & 255;
+  u32 ex[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) ex[r] = 2 * (__brev((u32)unphys(4 * tp + r)) >> (32 - LOGN)) + 1; // slot = X -> psi^ex
+  const int pg0 = 2 * pair, pgn = max(0, min(2, gcount - pg0)); // this pair's gates
+  const u32 qinv = P.qinv_neg;
+
+  auto close_step = [&]() { // inverse transform of the previous product, accumulate, publish
+    u32 x[16];
+    ntt_inverse_split<2>(x, myrow, P, tt, T, poly_bar);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      u32 a = mydp[T + 64 * k] - DIGIT_OFF;       // centred value, two's complement
+      a += ((int)a < 0) ? Q : 0u;                 // back to [0,Q)
+      a = csub(a + x[k], Q);
+      mydp[T + 64 * k] = ((a < (Q >> 1)) ? a : a - Q) + DIGIT_OFF;
+    }
+  };
+
+  for (u32 step = 0; step < n; step++) {
+    // ================= phase A: transforms (integer pipes) =================
+    if (gvalid) {
+      if (step > 0) close_step();
+      bar_sync(poly_bar, 64); // both halves of dp visible; nobody still reads row c
+#pragma unroll 1
+      for (int l = 2 * h; l < 2 * h + 2; l++) ntt_forward_digit(mydp, l, dct + ((size_t)g * ROWS + c + 2 * l) * N, P, tt, lane);
+    }
+    const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + 4 * tp;
+    if constexpr (!MAC_FP64) {
+      uint4 kr[2][ROWS];
+      if (pgn > 0) {
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+#pragma unroll
+          for (int r = 0; r < ROWS; r++) kr[s][r] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((s * ROWS + r) * 2 + 0) * N));
+      }
+      bar_sync(pair_bar, 256);
+      // ================= phase B: external product =================
+      u32 out0[2][4];
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) {
+        if (cc == 1 && pgn > 0) {
+#pragma unroll
+          for (int s = 0; s < 2; s++)
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) kr[s][r] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((s * ROWS + r) * 2 + 1) * N));
+        }
+#pragma unroll
+        for (int gl = 0; gl < 2; gl++) {
+          if (gl >= pgn) continue;
+          u32 *gd = dct + (size_t)(pg0 + gl) * ROWS * N + 4 * tp;
+          u64 sp[4] = {0, 0, 0, 0}, sn[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int r = 0; r < ROWS; r++) {
+            const uint4 dv = *reinterpret_cast<const uint4 *>(gd + (size_t)r * N);
+            const uint4 kp = kr[0][r], kn = kr[1][r];
+            sp[0] += (u64)dv.x * kp.x; sp[1] += (u64)dv.y * kp.y; sp[2] += (u64)dv.z * kp.z; sp[3] += (u64)dv.w * kp.w;
+            sn[0] += (u64)dv.x * kn.x; sn[1] += (u64)dv.y * kn.y; sn[2] += (u64)dv.z * kn.z; sn[3] += (u64)dv.w * kn.w;
+          }
+          const u32 m = s_idx[(pg0 + gl) * NPAD + step];
+          u32 out[4];
+#pragma unroll
+          for (int sl = 0; sl < 4; sl++) {
+            const u32 y = m * ex[sl], ny = 0u - y;
+            const u32 fp = s_F[f_index(y)], fn = s_F[f_index(ny)]; // (X^m - 1), (X^-m - 1) at this slot, Montgomery form
+            out[sl] = redc((u64)redc(sp[sl], Q, qinv) * fp + (u64)redc(sn[sl], Q, qinv) * fn, Q, qinv);
+          }
+          if (cc == 0) {
+#pragma unroll
+            for (int sl = 0; sl < 4; sl++) out0[gl][sl] = out[sl];
+          } else { // R[g][0], R[g][1] overwrite rows 0 and 1: this thread has consumed these four slots of every row
+            *reinterpret_cast<uint4 *>(gd) = make_uint4(out0[gl][0], out0[gl][1], out0[gl][2], out0[gl][3]);
+            *reinterpret_cast<uint4 *>(gd + (size_t)N) = make_uint4(out[0], out[1], out[2], out[3]);
+          }
+        }
+      }
+    } else {
+      bar_sync(pair_bar, 256);
+      // FP64 form: slot-parallel (one slot per thread at a time); see mac_fp64 below
+      // (filled in by the MAC_FP64 specialisation)
+    }
+    bar_sync(pair_bar, 256);
+  }
+
+  // ---- epilogue: last inverse transform, sample extraction (a14) and ModSwitch Q -> qKS (a15) ----
+  if (gvalid) {
+    if (n > 0) close_step();
+    const size_t gi = (size_t)gate0 + g;
+    u32 *e = ext + gi * (N + 4);
+    const u64 qKS = P.qKS;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const u32 j = T + 64 * k;
+      u32 a = mydp[j] - DIGIT_OFF;
+      a += ((int)a < 0) ? Q : 0u;
+      if (acc_dbg) acc_dbg[(gi * 2 + c) * N + j] = a;
+      if (c == 0) {
+        const u32 v = (j == 0) ? a : (a == 0 ? 0 : Q - a); // Transpose: a'_0 = a_0, a'_k = -a_{N-k}
+        e[(j == 0) ? 0 : N - j] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+      } else if (j == 0) {
+        const u32 v = csub(a + P.Q8, Q);
+        e[N] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+      }
+    }
+  }
+}
+
+// bootstrapping key: [chunk][lane][4] order of kernels.cu -> physical row order of this kernel (word phys(p) = slot p)
+__global__ void bk_permute_v2_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t npoly) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npoly * N; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t poly = i / N;
+    const int p = (int)(i % N), t = p >> 5, j = p & 31;
+    dst[poly * N + phys(p)] = src[poly * N + ((j >> 2) * 32 + t) * 4 + (j & 3)];
+  }
+}
+
+} // namespace v2
+
+bool v2_supported(const DevConst &P, int method_ap) {
+  return !method_ap && P.N == 1024 && P.dG == 4 && P.logBG == 7 && P.Q == v2::SOLINAS_Q && P.n <= (u32)v2::NPAD;
+}
+int v2_set_attrs() {
+  return (int)cudaFuncSetAttribute(v2::blind_rotate_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cfg::smem_bytes);
+}
+int launch_bk_permute_v2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
+  if (npoly == 0) return 0;
+  v2::bk_permute_v2_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly);
+  return (int)cudaGetLastError();
+}
+int launch_blind_rotate_v2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
+                           LaunchInfo *info) {
+  if (count <= 0) return 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    int rc = v2_set_attrs();
+    if (rc) return rc;
+    attr_done = true;
+  }
+  const int ctas = (count + v2::G - 1) / v2::G;
+  if (info) { info->gates_per_cta = v2::G; info->ctas = ctas; info->smem_bytes = v2::Cfg::smem_bytes; }
+  v2::blind_rotate_v2_kernel<false><<<ctas, v2::THREADS, v2::Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk2, vb.d_tw2, vb.d_F,
+                                                                                                  d_ext, d_acc_dbg);
+  return (int)cudaGetLastError();
+}
+
+} // namespace bfhe

@@ -389,7 +389,7 @@ static int enqueue_levels(bfhe_circuit *c) {
     const uint32_t n = c->my_count[L];
     if (n) {
       int rc = launch_blind_rotate(x->P, x->p.method == BFHE_AP, c->d_desc + c->desc_off[L], (int)n, x->d_bk, x->d_twl, x->d_psiM,
-                                   c->d_ext, nullptr, x->force_g, x->stream, nullptr);
+                                   c->d_ext, nullptr, x->force_g, x->stream, nullptr, &x->v2);
       if (rc) return cuda_fail((cudaError_t)rc, "blind_rotate launch");
       rc = launch_keyswitch(x->P, c->d_ext, c->d_desc + c->desc_off[L], (int)n, x->d_ksk, x->ksk_elem_bytes, x->stream);
       if (rc) return cuda_fail((cudaError_t)rc, "keyswitch launch");
