@@ -8,13 +8,19 @@ if os.environ.get('BFHE_LIB'):
     B.LIB_PATH = os.path.join(os.path.dirname(B.LIB_PATH), os.environ['BFHE_LIB'])
 ctx = B.Context(B.STD128_OPT, B.GINX, 0)
 ctx.keygen(1); ctx.btkeygen(2)
-for count in (1, 148):
+for count in [int(a) for a in os.environ.get('COUNTS', '1,148').split(',')]:
     bits = np.random.default_rng(0).integers(0, 2, 2 * count)
     slab = ctx.slab(3 * count); slab.upload(ctx.encrypt(bits, seed=1))
     g = np.zeros(count, dtype=B.GATE_DTYPE)
     g["op"] = B.NAND; g["in0"] = 2 * np.arange(count); g["in1"] = 2 * np.arange(count) + 1; g["out"] = 2 * count + np.arange(count)
     ctx.dbg_set_gates_per_cta(int(os.environ.get('GPC', '8')))
     acc = ctx.dbg_blind_rotate(slab, g)
+    if os.environ.get('GPC') == '16':  # kernels_v2.cu: [gate][component][32 + 8*h + phase]
+        for h in (0, 1):
+            t = acc[:, :, 32 + 8 * h:37 + 8 * h].astype(np.float64)
+            names = ["intt+publish+polybar", "fwd ntt x2", "keyload+pairbar1", "mac", "pairbar2"]
+            print(count, "gates, h", h, {n: round(float(v), 1) for n, v in zip(names, t.mean((0, 1)))}, "total kcyc", round(float(t.sum(2).mean()), 1))
+        continue
     t = acc[:, :, 32:37].astype(np.float64)  # kilo-cycles per phase, warps 0 and 1
     names = ["intt+decompose", "barrier1", "ntt", "barrier2+keywait", "mac"]
     for w in (0, 1):
