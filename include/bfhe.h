@@ -132,6 +132,10 @@ int bfhe_circuit_info(const bfhe_circuit *, uint32_t *n_inputs, uint32_t *input_
 /* multi-GPU: shard every level over world ranks; comm_id = 128-byte ncclUniqueId distributed by the caller */
 int bfhe_circuit_set_sharding(bfhe_circuit *, int rank, int world, const void *nccl_unique_id);
 int bfhe_get_nccl_unique_id(void *out128);
+/* schedule: 0 = the reference's ASAP waves (src/circuit.cpp:593-677), one launch per level; n > 0 = ready gates packed into
+ * waves of at most n bootstraps by longest remaining path; -1 (default) = one gate per SM and rank when a device is attached,
+ * ASAP otherwise.  Ciphertexts do not depend on the schedule.  bfhe_circuit_info always reports the ASAP statistics. */
+int bfhe_circuit_set_wave_capacity(bfhe_circuit *, int max_bootstraps_per_wave);
 int bfhe_circuit_reset(bfhe_circuit *);                                     /* Circuit::Reset */
 int bfhe_circuit_set_input(bfhe_circuit *, const uint8_t *bits, size_t nbits, uint64_t seed); /* Circuit::SetInput (all input buses concatenated) */
 int bfhe_circuit_clock(bfhe_circuit *, uint8_t *out_bits, size_t cap, uint8_t *plain_out_bits); /* Circuit::Clock */

@@ -47,6 +47,7 @@ ABI_SYMBOLS = [
     "bfhe_dbg_ntt_roundtrip", "bfhe_dbg_blind_rotate", "bfhe_dbg_set_gates_per_cta",
     "bfhe_circuit_create", "bfhe_circuit_destroy", "bfhe_circuit_read_file", "bfhe_circuit_read_bristol",
     "bfhe_circuit_set_flags", "bfhe_circuit_info", "bfhe_circuit_set_sharding", "bfhe_get_nccl_unique_id",
+    "bfhe_circuit_set_wave_capacity",
     "bfhe_circuit_reset", "bfhe_circuit_set_input", "bfhe_circuit_clock", "bfhe_circuit_stats",
     "bfhe_circuit_level_plan", "bfhe_circuit_plan_misc", "bfhe_circuit_use_graph", "bfhe_circuit_download_slab",
     "bfhe_circuit_dump_gate_count", "bfhe_circuit_load_netlist", "bfhe_circuit_get_netlist", "bfhe_circuit_write_out",
@@ -105,6 +106,7 @@ def lib():
     L.bfhe_circuit_set_flags.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.bfhe_circuit_info.argtypes = [vp, u32p, u32p, u32p, u32p, u32p, u32p, u32p]
     L.bfhe_circuit_set_sharding.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.bfhe_circuit_set_wave_capacity.argtypes = [vp, C.c_int]
     L.bfhe_get_nccl_unique_id.argtypes = [vp]
     L.bfhe_circuit_reset.argtypes = [vp]
     L.bfhe_circuit_set_input.argtypes = [vp, vp, sz, C.c_uint64]
@@ -416,6 +418,10 @@ class Circuit:
         self._flags = [False, False, False]  # src/circuit.cpp:378-381
         self._push_flags()
         self._ck(self.L.bfhe_circuit_reset(self.h))
+
+    def set_wave_capacity(self, cap):
+        """0 = the reference's ASAP waves; n > 0 = ready gates packed into waves of <= n bootstraps; -1 = one gate per SM and rank."""
+        self._ck(self.L.bfhe_circuit_set_wave_capacity(self.h, cap))
 
     def set_sharding(self, rank, world, unique_id=None):
         self._ck(self.L.bfhe_circuit_set_sharding(self.h, rank, world, _ptr(unique_id)))

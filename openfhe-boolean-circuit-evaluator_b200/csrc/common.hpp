@@ -29,7 +29,6 @@ struct DevConst {
   u32 gate_const[9];
   // psi^bitrev(k), k in [1,32): the twiddles of every NTT stage whose butterflies span >= 32 indices.
   u32 tw[32], tws[32], itw[32], itws[32];
-  double twd[16]; // tw[k] as centred doubles, k < 16: uniform twiddles of the FP64 transforms (kernels_v2.cu)
 };
 
 // one gate as the kernels see it (built on the host from bfhe_gate)
@@ -53,13 +52,12 @@ struct LaunchInfo { // filled by the launch helpers for the profiler hooks
 // device buffers of the second-generation throughput kernel (kernels_v2.cu); all null when the parameter set is not covered
 struct V2Bufs {
   const u32 *d_bk2 = nullptr; // bootstrapping key, rows in the kernel's physical slot order
-  const u32 *d_tw2 = nullptr; // fwd w | fwd ws | inv w | inv ws (each N words) | fwd w as N centred doubles
+  const u32 *d_tw2 = nullptr; // fwd w | fwd ws | inv w | inv ws, each N words (order: kernels_v2.cu Tabs)
   const u32 *d_F = nullptr;   // (psi^k - 1) * 2^32 mod Q, k < 2N
 };
 
 // kernels.cu entry points (all asynchronous on `stream`; return cudaError_t as int)
 // force_gates_per_cta: 0 = cost model; 1, 2, 4 = first-generation throughput form; 8 = latency form; 16 = second-generation form
-// (all transforms on the integer pipes), 17 = second-generation form with one digit transform per warp on the FP64 pipe
 int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates, int count, const u32 *d_bk,
                         const u32 *d_twl /*fwd w | fwd ws | inv w | inv ws, each N words*/, const u32 *d_psiM,
                         u32 *d_ext /*count * (N+4)*/, u32 *d_acc_dbg /*nullable: count*2*N*/, int force_gates_per_cta,
@@ -69,9 +67,7 @@ bool v2_supported(const DevConst &P, int method_ap);
 int v2_set_attrs();
 int launch_bk_permute_v2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
 int launch_blind_rotate_v2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
-                           void *stream, LaunchInfo *info, bool ntt_fp64);
-int v2_tw_words();
-int v2_twd_index(int m, int i); // slot of twiddle (m groups, group i) in the double table
+                           void *stream, LaunchInfo *info);
 int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates, int count, const void *d_ksk,
                      int ksk_elem_bytes, void *stream);
 int launch_eval_not(const DevConst &P, const u32 *const *d_in, u32 *const *d_out, int count, void *stream);

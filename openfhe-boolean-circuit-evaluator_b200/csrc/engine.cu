@@ -102,7 +102,6 @@ extern "C" bfhe_ctx *bfhe_create(int paramset, int method, int device) {
   P.gate_const[BFHE_OR] = 5 * (q >> 3); P.gate_const[BFHE_AND] = 7 * (q >> 3); P.gate_const[BFHE_NOR] = q >> 3;
   P.gate_const[BFHE_NAND] = 3 * (q >> 3); P.gate_const[BFHE_XOR_FAST] = 5 * (q >> 3); P.gate_const[BFHE_XNOR_FAST] = q >> 3;
   P.gate_const[BFHE_XOR] = P.gate_const[BFHE_XNOR] = 0; P.gate_const[BFHE_BOOTSTRAP] = 7 * (q >> 3);
-  for (int k = 0; k < 16; k++) P.twd[k] = c->hntt.tw[k] > Q / 2 ? (double)c->hntt.tw[k] - (double)Q : (double)c->hntt.tw[k];
   for (int k = 0; k < 32; k++) {
     P.tw[k] = c->hntt.tw[k]; P.tws[k] = shoup32(P.tw[k], Q);
     P.itw[k] = c->hntt.itw[k]; P.itws[k] = shoup32(P.itw[k], Q);
@@ -153,20 +152,13 @@ extern "C" bfhe_ctx *bfhe_create(int paramset, int method, int device) {
               cudaEventCreateWithFlags(&c->stage_ev[0], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->stage_ev[1], cudaEventDisableTiming) == cudaSuccess;
     if (ok && v2_supported(P, method == BFHE_AP)) { // tables of the second-generation throughput kernel
-      std::vector<u32> t2((size_t)v2_tw_words()), F(2 * (size_t)N);
+      std::vector<u32> t2(4 * (size_t)N), F(2 * (size_t)N);
       for (u32 k = 0; k < N; k++) { // natural order, last stage de-interleaved (kernels_v2.cu load_tw_narrow)
         u32 d = k;
         if (k >= N / 2) { const u32 i = k - N / 2, t = i >> 3, j = i & 7; d = N / 2 + (N / 4) * (j >> 2) + 4 * t + (j & 3); }
         t2[d] = c->hntt.tw[k]; t2[N + d] = shoup32(c->hntt.tw[k], Q);
         t2[2 * N + d] = c->hntt.itw[k]; t2[3 * N + d] = shoup32(c->hntt.itw[k], Q);
       }
-      double *twd = reinterpret_cast<double *>(t2.data() + 4 * (size_t)N); // forward twiddles as centred doubles
-      for (u32 m = 1; m < N; m <<= 1)
-        for (u32 i = 0; i < m; i++) {
-          const u32 w = c->hntt.tw[m + i];
-          twd[v2_twd_index((int)m, (int)i)] = w > Q / 2 ? (double)w - (double)Q : (double)w;
-        }
-      twd[0] = 0.0;
       const u64 oneM = (1ull << 32) % Q;
       for (u32 k = 0; k < 2 * N; k++) // (psi^k - 1) in Montgomery form, stored at the 11-bit rotation of k (kernels_v2.cu f_index)
         F[((k >> 5) & 63u) | ((k & 31u) << 6)] = (u32)((psiM[k] + Q - oneM) % Q);

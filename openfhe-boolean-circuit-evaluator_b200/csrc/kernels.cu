@@ -1049,7 +1049,7 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   if (count <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const bool have_v2 = v2 && v2->d_bk2 && v2_supported(P, method_ap);
-  if ((force_g == 16 || force_g == 17) && !have_v2) return (int)cudaErrorInvalidValue;
+  if (force_g == 16 && !have_v2) return (int)cudaErrorInvalidValue;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1059,7 +1059,7 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   const long lat_cost = (long)((count + sms - 1) / sms) * 23;
   const long thr_cost = (long)((count + 4 * sms - 1) / (4 * sms)) * 76;
   const bool lat = force_g == 8 || (force_g == 0 && lat_cost <= thr_cost);
-  if (force_g == 16 || force_g == 17) return launch_blind_rotate_v2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info, force_g == 17);
+  if (force_g == 16) return launch_blind_rotate_v2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   if (lat) {
     if (P.N == 1024 && P.dG == 4 && P.logBG == 7)
       return method_ap ? launch_lat_inst<10, 4, 7, true>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
@@ -1069,7 +1069,7 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
                        : launch_lat_inst<9, 3, 9, false>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);
     return (int)cudaErrorInvalidValue;
   }
-  if (have_v2 && force_g == 0) return launch_blind_rotate_v2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info, false);
+  if (have_v2 && force_g == 0) return launch_blind_rotate_v2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   int G = force_g > 0 ? force_g : 4;
   if (P.N == 1024 && P.dG == 4 && P.logBG == 7) {
     return method_ap ? launch_br_g<10, 4, 7, true>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)

@@ -12,19 +12,13 @@
 //  * The accumulator lives in shared memory in "centred + digit offset" form (what the digit extraction consumes).
 //  * One shared-memory layout (phys()) serves all three register-tile shapes conflict-free: 32-bit column access,
 //    64-bit pair access, 128-bit row access (checked by tools/smem_layout_check.py).
-//  * NTT_FP64 = true: each warp runs ONE of its two digit transforms on the FP64 pipe (exact integer arithmetic in doubles,
-//    fp64 namespace below).  B200 issues DFMA at the IMAD rate on a pipe of its own (tools/pipe_probe.cu: 17.0 T DFMA/s next to
-//    18.5 T IMAD/s, and IMAD + DFMA pairs at the rate of either alone), and the integer transforms are bound by the FMA-heavy
-//    pipe, not by issue slots -- so the FP64 transforms ride along in the issue slots the integer ones leave empty.  Half of the
-//    warps of a scheduler start with their FP64 transform, the other half with their integer one.
-//    (The external product was evaluated for the same treatment and rejected: exactness needs the key split 14 + 13 bits, i.e.
-//    two DFMA per IMAD.WIDE plus per-word conversions, 2.5x the issue slots of the integer form -- DESIGN.md 5.4.)
+//  * Measured and not kept (git history: "Experiment: one digit transform per warp on the FP64 pipe"): running one of each
+//    warp's two digit transforms in exact double arithmetic on the FP64 pipe was bit-exact but 11 % slower.
+//    tools/pipe_probe.cu / tools/bfly_probe.cu show why: DFMA co-issues freely with IMAD but contends with IMAD.HI and
+//    IMAD.WIDE (the 64-bit-product forms appear to use the FP64 multiplier), so there is no idle pipe to move butterflies to.
 #include "common.hpp"
 #include <cuda_runtime.h>
 
-#ifndef BFHE_V2_BFLY
-#define BFHE_V2_BFLY 2 // measured on B200: 0 -> 78.3k, 1 -> 75.6k, 2 -> 79.5k, 3 -> 74.9k gates/s
-#endif
 namespace bfhe {
 namespace v2 {
 
@@ -32,7 +26,23 @@ constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, G = 4,
 constexpr u32 DIGIT_OFF = 64u + (64u << 7) + (64u << 14) + (64u << 21);
 constexpr u32 SOLINAS_Q = (1u << 27) - (1u << 11) + 1;
 
-__device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q) { return x * w - __umulhi(x, ws) * Q; } // [0,2Q)
+// SOL: the t*Q term of the Shoup multiply as shifts and adds on the ALU pipe (Q = 2^27 - 2^11 + 1: t*Q = t + ((t << 16) - t) << 11)
+// instead of one IMAD on the FMA-heavy pipe; chosen per butterfly stage by the BFHE_V2_SOL_* masks to balance the two pipes.
+template <bool SOL = false> __device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q) { // [0,2Q)
+  const u32 t = __umulhi(x, ws);
+  if constexpr (SOL) {
+    const u32 s = t - (t << 16);
+    return (x * w - t) + (s << 11);
+  } else {
+    return x * w - t * Q;
+  }
+}
+#ifndef BFHE_V2_SOL_FW
+#define BFHE_V2_SOL_FW 0x000 // bit i = forward stage i (0 = widest)
+#endif
+#ifndef BFHE_V2_SOL_INV
+#define BFHE_V2_SOL_INV 0x000 // bit i = inverse stage i (0 = narrowest)
+#endif
 __device__ __forceinline__ u32 redc(u64 s, u32 Q, u32 qinv_neg) { // s * 2^-32 mod Q, lazy
   const u32 m = (u32)s * qinv_neg;
   return (u32)((s + (u64)m * Q) >> 32);
@@ -58,33 +68,40 @@ __host__ __device__ __forceinline__ int unphys(int o) {
 // ---- butterfly stages on a 16-register tile -------------------------------------------------------------------------
 // Cooley-Tukey, half-sizes TBEG, TBEG/2, ..., TEND; group gi of the stage with half-size t uses twiddle w[16/(2t) + gi].
 // No range correction: values grow by 2Q per stage (21Q < 2^32 after all ten).
-template <int TBEG, int TEND>
+// Written batch-wise (all high products of a stage, then all low products, then the corrections, then the sums): ptxas keeps
+// close to source order inside these very long basic blocks, and butterfly-by-butterfly source order left every instruction
+// waiting on its predecessor (profiles/r1_v2_*: 27 % of warp cycles in fixed-latency "wait").
+template <int TBEG, int TEND, int SOLMASK = 0>
 __device__ __forceinline__ void ct_stages(u32 (&x)[16], const u32 *__restrict__ w, const u32 *__restrict__ ws, u32 Q, u32 Q2, u32 Z) {
+  int si = 0;
 #pragma unroll
-  for (int t = TBEG; t >= TEND; t >>= 1) {
+  for (int t = TBEG; t >= TEND; t >>= 1, si++) {
+    const bool sol = (SOLMASK >> si) & 1;
+    u32 hi[8], lo[8];
 #pragma unroll
-    for (int gi = 0; gi < 16 / (2 * t); gi++) {
-      const int p = 16 / (2 * t) + gi;
+    for (int i = 0; i < 8; i++) { // butterfly i: group gi = i / t, member j = i % t
+      const int gi = i / t, b = gi * 2 * t + (i % t) + t, p = 16 / (2 * t) + gi;
+      hi[i] = __umulhi(x[b], ws[p]);
+    }
 #pragma unroll
-      for (int j = 0; j < t; j++) {
-        const int a = gi * 2 * t + j, b = a + t;
-#if BFHE_V2_BFLY == 0
-        const u32 T = mul_shoup(x[b], w[p], ws[p], Q);
-        x[b] = x[a] - T + Q2;
-        x[a] = x[a] + T;
-#elif BFHE_V2_BFLY == 2
-        const u32 T = mul_shoup(x[b], w[p], ws[p], Q);
-        x[b] = x[a] - T + Q2;
-        x[a] = add3(x[a], T, Z);
-#else
-        // a' = x_a + (x_b*w - t*Q) as two multiply-adds with x_a riding in as the addend; b' = (2*x_a + 2Q) - a'
-        const u32 t = __umulhi(x[b], ws[p]);
-        const u32 s2 = (x[a] << 1) + Q2;
-        const u32 an = t * (0u - Q) + (x[b] * w[p] + x[a]);
-        x[a] = an;
-        x[b] = BFHE_V2_BFLY == 3 ? add3(s2, 0u - an, Z) : s2 - an;
-#endif
+    for (int i = 0; i < 8; i++) {
+      const int gi = i / t, b = gi * 2 * t + (i % t) + t, p = 16 / (2 * t) + gi;
+      lo[i] = x[b] * w[p];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (sol) {
+        const u32 s = hi[i] - (hi[i] << 16);
+        lo[i] = (lo[i] - hi[i]) + (s << 11);
+      } else {
+        lo[i] = lo[i] - hi[i] * Q;
       }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int gi = i / t, a = gi * 2 * t + (i % t), b = a + t;
+      x[b] = x[a] - lo[i] + Q2;
+      x[a] = add3(x[a], lo[i], Z);
     }
   }
 }
@@ -97,7 +114,7 @@ __host__ __device__ constexpr int gs_bound(int T, int TEND, int B, int MAXOUT) {
   }
   return B;
 }
-template <int T, int TEND, int B, int MAXOUT> struct Gs {
+template <int T, int TEND, int B, int MAXOUT, int SOLMASK = 0> struct Gs {
   static constexpr int NB = 2 * B;
   static constexpr bool LAST = (T == TEND);
   static constexpr bool RED = LAST ? (NB > MAXOUT) : (NB > 16);
@@ -105,23 +122,29 @@ template <int T, int TEND, int B, int MAXOUT> struct Gs {
   __device__ __forceinline__ static void run(u32 (&x)[16], const u32 *__restrict__ w, const u32 *__restrict__ ws, u32 Q, u32 Z) {
     static_assert(B <= 16, "GS input bound too large");
     const u32 off = B * Q;
+    u32 D[8], hi[8];
 #pragma unroll
-    for (int gi = 0; gi < 16 / (2 * T); gi++) {
-      const int p = 16 / (2 * T) + gi;
+    for (int i = 0; i < 8; i++) { // butterfly i: group gi = i / T, member j = i % T
+      const int gi = i / T, a = gi * 2 * T + (i % T), b = a + T;
+      D[i] = x[a] - x[b] + off;
+      const u32 S = add3(x[a], x[b], Z);
+      x[a] = RED ? lazy_reduce(S, Q) : S;
+    }
 #pragma unroll
-      for (int j = 0; j < T; j++) {
-        const int a = gi * 2 * T + j, b = a + T;
-#if BFHE_V2_BFLY >= 2
-        const u32 S = add3(x[a], x[b], Z);
-#else
-        const u32 S = x[a] + x[b];
-#endif
-        const u32 D = x[a] - x[b] + off;
-        x[b] = mul_shoup(D, w[p], ws[p], Q);
-        x[a] = RED ? lazy_reduce(S, Q) : S;
+    for (int i = 0; i < 8; i++) hi[i] = __umulhi(D[i], ws[16 / (2 * T) + i / T]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) D[i] = D[i] * w[16 / (2 * T) + i / T];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int gi = i / T, b = gi * 2 * T + (i % T) + T;
+      if ((SOLMASK & 1) != 0) {
+        const u32 s = hi[i] - (hi[i] << 16);
+        x[b] = (D[i] - hi[i]) + (s << 11);
+      } else {
+        x[b] = D[i] - hi[i] * Q;
       }
     }
-    if constexpr (!LAST) Gs<2 * T, TEND, OUTB, MAXOUT>::run(x, w, ws, Q, Z);
+    if constexpr (!LAST) Gs<2 * T, TEND, OUTB, MAXOUT, (SOLMASK >> 1)>::run(x, w, ws, Q, Z);
   }
 };
 
@@ -200,155 +223,56 @@ __device__ __forceinline__ void row_store(u32 *buf, const u32 (&x)[16], int T3) 
 
 // forward transform of digit l of the accumulator component published in dp[] (centred + DIGIT_OFF, natural order), by ONE
 // warp (two 16-value tiles per pass); the result (bit-reversed evaluation order, lazy < 21Q) lands in row `buf`.
-__device__ __forceinline__ void ntt_forward_digit(const u32 *dp, int l, u32 *buf, const DevConst &P, const Tabs &tt, int lane, u32 Z) {
+// Digits l0 and l0 + 1 are transformed TOGETHER, tile by tile: the two tiles share the accumulator words they are cut from and
+// every per-thread twiddle, and give the scheduler 16 independent butterflies per stage instead of 8.
+__device__ __forceinline__ void ntt_forward_2digits(const u32 *dp, int l0, u32 *bufA, u32 *bufB, const DevConst &P, const Tabs &tt, int lane, u32 Z) {
   const u32 Q = P.Q, Q2 = P.Q2, qoff = P.Q - (1u << (LOGBG - 1)); // Z: a zero the compiler cannot see (add3)
+  const int sh = LOGBG * l0;
 #pragma unroll 1
   for (int it = 0; it < 2; it++) { // wide pass: positions T + 64k, stages with 1, 2, 4, 8 groups (uniform twiddles: constant bank)
     const int T = 32 * it + lane;
-    u32 x[16];
+    u32 xa[16], xb[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       // digit - B/2 + Q: congruent to the signed digit, lazy in (Q - B/2, Q + B/2) -- the transform needs no canonical input
-      x[k] = ((dp[T + 64 * k] >> (LOGBG * l)) & ((1u << LOGBG) - 1)) + qoff;
+      const u32 d = dp[T + 64 * k] >> sh;
+      xa[k] = (d & ((1u << LOGBG) - 1)) + qoff;
+      xb[k] = ((d >> LOGBG) & ((1u << LOGBG) - 1)) + qoff;
     }
-    ct_stages<8, 1>(x, P.tw, P.tws, Q, Q2, Z);
-    col_store(buf, x, T);
+    ct_stages<8, 1, (BFHE_V2_SOL_FW & 15)>(xa, P.tw, P.tws, Q, Q2, Z);
+    ct_stages<8, 1, (BFHE_V2_SOL_FW & 15)>(xb, P.tw, P.tws, Q, Q2, Z);
+    col_store(bufA, xa, T);
+    col_store(bufB, xb, T);
   }
   __syncwarp();
 #pragma unroll 1
   for (int it = 0; it < 2; it++) { // middle pass, in place
     const int T = 32 * it + lane;
-    u32 x[16], w[16], ws[16];
+    u32 xa[16], xb[16], w[16], ws[16];
     load_tw_mid(tt.fw, w, T >> 2);
     load_tw_mid(tt.fws, ws, T >> 2);
-    mid_load(buf, x, T);
-    ct_stages<8, 2>(x, w, ws, Q, Q2, Z);
-    mid_store(buf, x, T);
+    mid_load(bufA, xa, T);
+    mid_load(bufB, xb, T);
+    ct_stages<8, 2, ((BFHE_V2_SOL_FW >> 4) & 7)>(xa, w, ws, Q, Q2, Z);
+    ct_stages<8, 2, ((BFHE_V2_SOL_FW >> 4) & 7)>(xb, w, ws, Q, Q2, Z);
+    mid_store(bufA, xa, T);
+    mid_store(bufB, xb, T);
   }
   __syncwarp();
 #pragma unroll 1
   for (int it = 0; it < 2; it++) { // narrow pass, in place
     const int T = 32 * it + lane;
-    u32 x[16], w[16], ws[16];
+    u32 xa[16], xb[16], w[16], ws[16];
     load_tw_narrow(tt.fw, w, T);
     load_tw_narrow(tt.fws, ws, T);
-    row_load(buf, x, T);
-    ct_stages<4, 1>(x, w, ws, Q, Q2, Z);
-    row_store(buf, x, T);
+    row_load(bufA, xa, T);
+    row_load(bufB, xb, T);
+    ct_stages<4, 1, ((BFHE_V2_SOL_FW >> 7) & 7)>(xa, w, ws, Q, Q2, Z);
+    ct_stages<4, 1, ((BFHE_V2_SOL_FW >> 7) & 7)>(xb, w, ws, Q, Q2, Z);
+    row_store(bufA, xa, T);
+    row_store(bufB, xb, T);
   }
 }
-
-// ---- the same forward transform on the FP64 pipe ---------------------------------------------------------------------
-// Values are exact integers held in doubles, centred representatives, never reduced to a canonical range:
-//   cheap  T = x*w - rint(x*w/Q)*Q               4 ops, exact while |x*w| < 2^53 (|w| <= Q/2 < 2^26, so |x| < 2^27: stages 0-2)
-//   exact  h = x*w (rounded); qs = rint(h/Q)*2^27 (magic-number rounding at 2^27 granularity);
-//          T = fma(qs, 2047/2^27, fma(x, w, -qs)) 5 ops: x*w - q*2^27 is an integer below 2^42, hence exact, and
-//          q*Q = q*2^27 - 2047*q for the Solinas modulus
-// |T| <= Q/2 + 2, so |x| <= 64 + 10*(Q/2 + 2) < 5.1 Q after the ten stages.  Between passes (and at the end) values travel
-// through the same shared-memory rows as 32-bit words x + 8Q in (2.9Q, 13.1Q).
-namespace fp64 {
-constexpr double QD = 134215681.0, QINV = 1.0 / 134215681.0, M52 = 6755399441055744.0; // 1.5 * 2^52
-constexpr double TWO27 = 134217728.0, QINV27 = TWO27 / QD, M79 = M52 * TWO27, C2047 = 2047.0 / TWO27;
-constexpr double TWO52 = 4503599627370496.0, BIAS = TWO52 + 8.0 * QD, DIGIT_BIAS = TWO52 + 64.0;
-__device__ __forceinline__ double from_u32(u32 v, double bias) { return __dadd_rn(__hiloint2double(0x43300000, (int)v), -bias); }
-__device__ __forceinline__ u32 to_u32(double x, double bias) { return (u32)__double2loint(__dadd_rn(x, bias)); }
-template <bool EXACT> __device__ __forceinline__ double mulmod(double x, double w) {
-  if constexpr (!EXACT) {
-    const double p = __dmul_rn(x, w);
-    const double q = __dadd_rn(__fma_rn(p, QINV, M52), -M52);
-    return __fma_rn(-q, QD, p);
-  } else {
-    const double h = __dmul_rn(x, w);
-    const double qs = __dadd_rn(__fma_rn(h, QINV27, M79), -M79);
-    return __fma_rn(qs, C2047, __fma_rn(x, w, -qs));
-  }
-}
-template <int TBEG, int TEND, int NCHEAP>
-__device__ __forceinline__ void ct_stages(double (&x)[16], const double *__restrict__ w) {
-  int si = 0;
-#pragma unroll
-  for (int t = TBEG; t >= TEND; t >>= 1, si++) {
-#pragma unroll
-    for (int gi = 0; gi < 16 / (2 * t); gi++) {
-      const int p = 16 / (2 * t) + gi;
-#pragma unroll
-      for (int j = 0; j < t; j++) {
-        const int a = gi * 2 * t + j, b = a + t;
-        const double T = si < NCHEAP ? mulmod<false>(x[b], w[p]) : mulmod<true>(x[b], w[p]);
-        x[b] = __dadd_rn(x[a], -T);
-        x[a] = __dadd_rn(x[a], T);
-      }
-    }
-  }
-}
-// twiddle table (doubles, centred): natural order m + i up to the 64-group stage; the stages of the narrow pass (m = 128, 256,
-// 512; thread T3 needs groups cnt*T3 + j, cnt = m/64) are stored as 16-byte pairs, pair j>>1 of all threads contiguous:
-__host__ __device__ __forceinline__ int tw_index(int m, int i) {
-  if (m < 128) return m + i;
-  const int cnt = m / 64, T3 = i / cnt, j = i % cnt;
-  return m + (j >> 1) * 128 + 2 * T3 + (j & 1);
-}
-__device__ __forceinline__ void load_tw_mid(const double *tab, double (&w)[16], int u) {
-  w[1] = tab[16 + u];
-  const double2 a = *reinterpret_cast<const double2 *>(tab + 32 + 2 * u);
-  w[2] = a.x; w[3] = a.y;
-  const double2 b = *reinterpret_cast<const double2 *>(tab + 64 + 4 * u), c = *reinterpret_cast<const double2 *>(tab + 64 + 4 * u + 2);
-  w[4] = b.x; w[5] = b.y; w[6] = c.x; w[7] = c.y;
-}
-__device__ __forceinline__ void load_tw_narrow(const double *tab, double (&w)[16], int T3) {
-#pragma unroll
-  for (int m = 128, base = 2; m <= 512; m *= 2, base *= 2)
-#pragma unroll
-    for (int pr = 0; pr < base / 2; pr++) {
-      const double2 v = *reinterpret_cast<const double2 *>(tab + m + pr * 128 + 2 * T3);
-      w[base + 2 * pr] = v.x; w[base + 2 * pr + 1] = v.y;
-    }
-}
-__device__ __forceinline__ void ntt_forward_digit(const u32 *dp, int l, u32 *buf, const DevConst &P, const double *twd, int lane) {
-#pragma unroll 1
-  for (int it = 0; it < 2; it++) {
-    const int T = 32 * it + lane;
-    double x[16];
-    u32 v[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = from_u32((dp[T + 64 * k] >> (LOGBG * l)) & ((1u << LOGBG) - 1), DIGIT_BIAS);
-    ct_stages<8, 1, 3>(x, P.twd);
-#pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = to_u32(x[k], BIAS);
-    col_store(buf, v, T);
-  }
-  __syncwarp();
-#pragma unroll 1
-  for (int it = 0; it < 2; it++) {
-    const int T = 32 * it + lane;
-    double x[16], w[16];
-    u32 v[16];
-    load_tw_mid(twd, w, T >> 2);
-    mid_load(buf, v, T);
-#pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = from_u32(v[k], BIAS);
-    ct_stages<8, 2, 0>(x, w);
-#pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = to_u32(x[k], BIAS);
-    mid_store(buf, v, T);
-  }
-  __syncwarp();
-#pragma unroll 1
-  for (int it = 0; it < 2; it++) {
-    const int T = 32 * it + lane;
-    double x[16], w[16];
-    u32 v[16];
-    load_tw_narrow(twd, w, T);
-    row_load(buf, v, T);
-#pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = from_u32(v[k], BIAS);
-    ct_stages<4, 1, 0>(x, w);
-#pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = to_u32(x[k], BIAS);
-    row_store(buf, v, T);
-  }
-}
-} // namespace fp64
 
 // inverse transform (unscaled; the keys carry N^-1) of row `buf` (values < B0*Q) by TWO warps, T = 32*h + lane; on return
 // x[k] = coefficient T + 64k, fully reduced.  bar_id: named barrier of this warp pair.
@@ -359,7 +283,7 @@ template <int B0> __device__ __forceinline__ void ntt_inverse_split(u32 (&x)[16]
     load_tw_narrow(tt.iw, w, T);
     load_tw_narrow(tt.iws, ws, T);
     row_load(buf, x, T);
-    Gs<1, 4, B0, 16>::run(x, w, ws, Q, Z);
+    Gs<1, 4, B0, 16, (BFHE_V2_SOL_INV & 7)>::run(x, w, ws, Q, Z);
     row_store(buf, x, T);
   }
   constexpr int B1 = gs_bound(1, 4, B0, 16);
@@ -369,13 +293,13 @@ template <int B0> __device__ __forceinline__ void ntt_inverse_split(u32 (&x)[16]
     load_tw_mid(tt.iw, w, T >> 2);
     load_tw_mid(tt.iws, ws, T >> 2);
     mid_load(buf, x, T);
-    Gs<2, 8, B1, 16>::run(x, w, ws, Q, Z);
+    Gs<2, 8, B1, 16, ((BFHE_V2_SOL_INV >> 3) & 7)>::run(x, w, ws, Q, Z);
     mid_store(buf, x, T);
   }
   constexpr int B2 = gs_bound(2, 8, B1, 16);
   bar_sync(bar_id, 64);
   col_load(buf, x, T);
-  Gs<1, 8, B2, 32>::run(x, P.itw, P.itws, Q, Z);
+  Gs<1, 8, B2, 32, ((BFHE_V2_SOL_INV >> 6) & 15)>::run(x, P.itw, P.itws, Q, Z);
 #pragma unroll
   for (int k = 0; k < 16; k++) x[k] = csub(lazy_reduce(x[k], Q), Q);
 }
@@ -387,12 +311,11 @@ __host__ __device__ __forceinline__ u32 f_index(u32 k) { return ((k >> 5) & 63u)
 struct Cfg {
   static constexpr size_t dct_words = (size_t)G * ROWS * N;  // [gate][row][phys]
   static constexpr size_t dp_words = (size_t)G * 2 * N;      // [gate][component][natural]
-  static constexpr size_t tw_words = 6 * N;                  // fw | fws | iw | iws | fw as doubles (fp64::tw_index order)
+  static constexpr size_t tw_words = 4 * N;                  // fw | fws | iw | iws
   static constexpr size_t f_words = 2 * N;                   // (psi^k - 1) in Montgomery form
   static constexpr size_t smem_bytes = (dct_words + dp_words + tw_words + f_words) * 4 + (size_t)G * NPAD * 2;
 };
 
-template <bool NTT_FP64>
 __global__ void __launch_bounds__(THREADS, 1)
 blind_rotate_v2_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count, const u32 *__restrict__ bk,
                        const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
@@ -416,7 +339,6 @@ blind_rotate_v2_kernel(const __grid_constant__ DevConst P, const DevGate *__rest
   for (int i = tid; i < (int)Cfg::tw_words; i += THREADS) s_tw[i] = g_tw[i];
   for (int i = tid; i < 2 * N; i += THREADS) s_F[i] = g_F[i];
   const Tabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
-  const double *s_twd = reinterpret_cast<const double *>(s_tw + 4 * N);
 
   // ---- prologue: LWE prep (EvalBinGate's ct1+ct2 / 2(ct1-ct2) / Bootstrap's b+q/4, with fused EvalNOT), as in kernels.cu ----
   for (int gg = 0; gg < gcount; gg++) {
@@ -499,15 +421,7 @@ blind_rotate_v2_kernel(const __grid_constant__ DevConst P, const DevGate *__rest
       if (step > 0) close_step();
       bar_sync(poly_bar, 64); // both halves of dp visible; nobody still reads row c
       PH_T(0);
-      if constexpr (NTT_FP64) { // one digit on the integer pipes, one on the FP64 pipe; gates alternate which comes first
-        const int lf = 2 * h + (g & 1), li = 2 * h + 1 - (g & 1);
-        if (g & 1) ntt_forward_digit(mydp, li, dct + ((size_t)g * ROWS + c + 2 * li) * N, P, tt, lane, Z);
-        fp64::ntt_forward_digit(mydp, lf, dct + ((size_t)g * ROWS + c + 2 * lf) * N, P, s_twd, lane);
-        if (!(g & 1)) ntt_forward_digit(mydp, li, dct + ((size_t)g * ROWS + c + 2 * li) * N, P, tt, lane, Z);
-      } else {
-#pragma unroll 1
-        for (int l = 2 * h; l < 2 * h + 2; l++) ntt_forward_digit(mydp, l, dct + ((size_t)g * ROWS + c + 2 * l) * N, P, tt, lane, Z);
-      }
+      ntt_forward_2digits(mydp, 2 * h, dct + ((size_t)g * ROWS + c + 4 * h) * N, dct + ((size_t)g * ROWS + c + 4 * h + 2) * N, P, tt, lane, Z);
     }
     PH_T(1);
     const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + 4 * tp;
@@ -615,19 +529,15 @@ bool v2_supported(const DevConst &P, int method_ap) {
   return !method_ap && P.N == 1024 && P.dG == 4 && P.logBG == 7 && P.Q == v2::SOLINAS_Q && P.n <= (u32)v2::NPAD;
 }
 int v2_set_attrs() {
-  int rc = (int)cudaFuncSetAttribute(v2::blind_rotate_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cfg::smem_bytes);
-  rc |= (int)cudaFuncSetAttribute(v2::blind_rotate_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cfg::smem_bytes);
-  return rc;
+  return (int)cudaFuncSetAttribute(v2::blind_rotate_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cfg::smem_bytes);
 }
-int v2_tw_words() { return (int)v2::Cfg::tw_words; }
-int v2_twd_index(int m, int i) { return v2::fp64::tw_index(m, i); }
 int launch_bk_permute_v2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
   if (npoly == 0) return 0;
   v2::bk_permute_v2_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly);
   return (int)cudaGetLastError();
 }
 int launch_blind_rotate_v2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
-                           LaunchInfo *info, bool ntt_fp64) {
+                           LaunchInfo *info) {
   if (count <= 0) return 0;
   static bool attr_done = false;
   if (!attr_done) {
@@ -637,12 +547,8 @@ int launch_blind_rotate_v2(const DevConst &P, const DevGate *d_gates, int count,
   }
   const int ctas = (count + v2::G - 1) / v2::G;
   if (info) { info->gates_per_cta = v2::G; info->ctas = ctas; info->smem_bytes = v2::Cfg::smem_bytes; }
-  if (ntt_fp64)
-    v2::blind_rotate_v2_kernel<true><<<ctas, v2::THREADS, v2::Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk2, vb.d_tw2, vb.d_F,
-                                                                                                   d_ext, d_acc_dbg);
-  else
-    v2::blind_rotate_v2_kernel<false><<<ctas, v2::THREADS, v2::Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk2, vb.d_tw2, vb.d_F,
-                                                                                                    d_ext, d_acc_dbg);
+  v2::blind_rotate_v2_kernel<<<ctas, v2::THREADS, v2::Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk2, vb.d_tw2, vb.d_F, d_ext,
+                                                                                           d_acc_dbg);
   return (int)cudaGetLastError();
 }
 

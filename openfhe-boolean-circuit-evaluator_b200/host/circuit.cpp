@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <queue>
 
 using namespace bfhe;
 
@@ -81,7 +82,9 @@ struct bfhe_circuit {
   uint32_t total_rows = 0, fresh_base = 0, n_in = 0;
   std::vector<uint32_t> in_wire_of_bit; // concatenated input bit -> wire
   std::vector<uint32_t> out_wire;       // output bit -> wire
-  uint32_t n_bootstraps = 0, max_width = 0;
+  uint32_t n_bootstraps = 0, max_width = 0, asap_levels = 0; // of the ASAP schedule (what the reference's manager produces)
+  uint32_t wave_cap = 0;             // > 0: pack ready gates into waves of at most this many bootstraps (build_plan pass 1b)
+  int wave_cap_req = -1;             // requested: -1 = one gate per SM and rank when a device is attached, 0 = ASAP levels, > 0 explicit
 
   // device state
   uint32_t *slab = nullptr;
@@ -120,6 +123,11 @@ static void free_device(bfhe_circuit *c) {
 // ---------------------------------------------------------------------------------------------
 static int build_plan(bfhe_circuit *c) {
   const Netlist &nl = c->nl;
+  c->wave_cap = c->wave_cap_req > 0 ? (uint32_t)c->wave_cap_req : 0;
+  if (c->wave_cap_req < 0 && c->ctx && c->ctx->device >= 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->ctx->device) == cudaSuccess && sms > 0) c->wave_cap = (uint32_t)sms * (uint32_t)c->world;
+  }
   const uint32_t NW = nl.n_wires, NG = (uint32_t)nl.gates.size();
   const uint32_t NONE = 0xffffffffu;
   std::vector<uint32_t> producer(NW, NONE);
@@ -180,9 +188,112 @@ static int build_plan(bfhe_circuit *c) {
   c->wire_neg.assign(NW, 0);
   c->wire_level.assign(NW, 0);
 
-  // pass 1: levels.  Rows are assigned afterwards, so gates carry (level, index) first.
-  struct Pending { uint32_t gate; uint32_t level; };
-  std::vector<std::vector<uint32_t>> lvl_gates(1); // netlist gate ids per bootstrap level (XOR appears at L and L+1)
+  // pass 1a: ASAP levels (the wave structure of the reference's manager): level of a gate = 1 + max(level of its
+  // producers); NOT costs nothing; XOR = two ANDs at L and the OR at L + 1.
+  std::vector<uint32_t> lvl1(NG, NONE), lvl2(NG, NONE); // bootstrap level of a gate's (first) bootstrap / of XOR's closing OR
+  for (uint32_t gi : c->topo) {
+    const NetGate &g = nl.gates[gi];
+    switch (g.kind) {
+    case GateKind::INPUT: c->wire_level[g.out] = 0; break;
+    case GateKind::NOT: c->wire_level[g.out] = c->wire_level[g.in0]; break;
+    case GateKind::AND: case GateKind::OR: case GateKind::XOR:
+      lvl1[gi] = 1 + std::max(c->wire_level[g.in0], c->wire_level[g.in1]);
+      if (g.kind == GateKind::XOR) lvl2[gi] = lvl1[gi] + 1;
+      c->wire_level[g.out] = g.kind == GateKind::XOR ? lvl2[gi] : lvl1[gi];
+      break;
+    case GateKind::OUTPUT: break;
+    }
+  }
+  { // the reference-shaped statistics always describe the ASAP schedule
+    std::vector<uint32_t> width(1, 0);
+    c->n_bootstraps = 0;
+    for (uint32_t gi = 0; gi < NG; gi++) {
+      if (lvl1[gi] == NONE) continue;
+      const bool x = nl.gates[gi].kind == GateKind::XOR;
+      if (width.size() <= lvl1[gi] + (x ? 1u : 0u)) width.resize(lvl1[gi] + (x ? 2 : 1), 0);
+      width[lvl1[gi]] += x ? 2 : 1;
+      if (x) width[lvl2[gi]] += 1;
+      c->n_bootstraps += x ? 3 : 1;
+    }
+    c->asap_levels = (uint32_t)width.size() - 1;
+    c->max_width = 0;
+    for (size_t L = 1; L < width.size(); L++) c->max_width = std::max(c->max_width, width[L]);
+  }
+  // pass 1b (wave_cap > 0): list scheduling into waves of at most wave_cap bootstraps.  An ASAP level of 196 gates costs
+  // two launches of the one-gate-per-SM kernel on 148 SMs although the second is a third full; packing ready gates by
+  // longest remaining path fills the waves (AES-128: 420 ASAP levels, 82 172 bootstraps -> ~560 full waves instead of ~790
+  // launches' worth).  Gate outputs do not depend on the schedule, so ciphertexts stay bit-identical.
+  if (c->wave_cap > 0) {
+    // units: U1 = the gate's first bootstrap(s) (weight 2 for XOR's AND pair), U2 = XOR's OR.  unit id = 2*gi (+1)
+    std::vector<uint32_t> wire_unit(NW, NONE);
+    std::vector<uint32_t> indeg(2 * (size_t)NG, 0), height(2 * (size_t)NG, 0);
+    std::vector<std::vector<uint32_t>> succ(2 * (size_t)NG);
+    for (uint32_t gi : c->topo) {
+      const NetGate &g = nl.gates[gi];
+      if (g.kind == GateKind::NOT) { wire_unit[g.out] = wire_unit[g.in0]; continue; }
+      if (lvl1[gi] == NONE) continue;
+      const uint32_t u1 = 2 * gi, u2 = 2 * gi + 1;
+      const uint32_t pa = wire_unit[g.in0], pb = wire_unit[g.in1];
+      if (pa != NONE) { succ[pa].push_back(u1); indeg[u1]++; }
+      if (pb != NONE && pb != pa) { succ[pb].push_back(u1); indeg[u1]++; }
+      if (g.kind == GateKind::XOR) { succ[u1].push_back(u2); indeg[u2]++; wire_unit[g.out] = u2; }
+      else wire_unit[g.out] = u1;
+    }
+    for (size_t k = c->topo.size(); k-- > 0;) { // longest path to a sink, in waves
+      const uint32_t gi = c->topo[k];
+      if (lvl1[gi] == NONE) continue;
+      for (uint32_t u : {2 * gi + 1, 2 * gi}) {
+        if (u == 2 * gi + 1 && nl.gates[gi].kind != GateKind::XOR) continue;
+        uint32_t h = 0;
+        for (uint32_t v : succ[u]) h = std::max(h, height[v]);
+        height[u] = h + 1;
+      }
+    }
+    auto weight = [&](uint32_t u) { return (u & 1) == 0 && nl.gates[u >> 1].kind == GateKind::XOR ? 2u : 1u; };
+    auto worse = [&](uint32_t a, uint32_t b) { return height[a] != height[b] ? height[a] < height[b] : a > b; };
+    std::priority_queue<uint32_t, std::vector<uint32_t>, decltype(worse)> ready(worse);
+    uint64_t ready_weight = 0;
+    for (uint32_t gi : c->topo) {
+      if (lvl1[gi] == NONE) continue;
+      if (indeg[2 * gi] == 0) { ready.push(2 * gi); ready_weight += weight(2 * gi); }
+    }
+    std::vector<uint32_t> wave_of(2 * (size_t)NG, NONE), next, held;
+    const uint32_t cap1 = c->wave_cap, cap4 = 4 * c->wave_cap; // one-gate-per-SM wave / four-gates-per-SM wave
+    for (uint32_t W = 1; !ready.empty(); W++) {
+      // plenty of independent work (at least two 4-gates-per-SM waves): use whole throughput-kernel waves, else one latency wave
+      uint32_t cap = ready_weight >= 2 * (uint64_t)cap4 ? (uint32_t)(ready_weight / cap4) * cap4 : cap1;
+      uint32_t used = 0;
+      next.clear(); held.clear();
+      while (!ready.empty() && used < cap) {
+        const uint32_t u = ready.top();
+        ready.pop();
+        const uint32_t wt = weight(u);
+        if (used + wt > cap) { held.push_back(u); if (held.size() > 8) break; continue; }
+        used += wt;
+        ready_weight -= wt;
+        wave_of[u] = W;
+        for (uint32_t v : succ[u]) if (--indeg[v] == 0) next.push_back(v);
+      }
+      for (uint32_t u : held) ready.push(u);
+      for (uint32_t v : next) { ready.push(v); ready_weight += weight(v); }
+    }
+    for (uint32_t gi : c->topo) {
+      const NetGate &g = nl.gates[gi];
+      switch (g.kind) {
+      case GateKind::INPUT: c->wire_level[g.out] = 0; break;
+      case GateKind::NOT: c->wire_level[g.out] = c->wire_level[g.in0]; break;
+      case GateKind::AND: case GateKind::OR: case GateKind::XOR:
+        lvl1[gi] = wave_of[2 * gi];
+        if (g.kind == GateKind::XOR) lvl2[gi] = wave_of[2 * gi + 1];
+        c->wire_level[g.out] = g.kind == GateKind::XOR ? lvl2[gi] : lvl1[gi];
+        break;
+      case GateKind::OUTPUT: break;
+      }
+    }
+  }
+
+  // pass 1c: placement.  Rows are assigned afterwards, so gates carry (level, index) first.
+  std::vector<std::vector<uint32_t>> lvl_gates(1); // netlist gate ids per bootstrap level (XOR appears at its two levels)
   struct Slot { uint32_t level, index; };
   std::vector<Slot> wire_slot(NW, Slot{NONE, NONE}); // for bootstrapped wires
   std::vector<Slot> xor_t1(NG, Slot{NONE, NONE});
@@ -197,29 +308,26 @@ static int build_plan(bfhe_circuit *c) {
       uint32_t bit = bus_base[g.in0] + g.in1;
       if (c->in_wire_of_bit[bit] != NONE) { set_error("input bit loaded twice"); return BFHE_ERR_FORMAT; }
       c->in_wire_of_bit[bit] = g.out;
-      c->wire_level[g.out] = 0;
       wire_slot[g.out] = Slot{0, bit};
       break;
     }
     case GateKind::NOT: {
-      c->wire_level[g.out] = c->wire_level[g.in0];
+      ensure_level(c->wire_level[g.in0]);
       if (c->verify || feeds_output[g.out]) lvl_nots[c->wire_level[g.in0]].push_back(gi);
       break;
     }
     case GateKind::AND: case GateKind::OR: case GateKind::XOR: {
-      uint32_t L = 1 + std::max(c->wire_level[g.in0], c->wire_level[g.in1]);
-      ensure_level(L + (g.kind == GateKind::XOR ? 1 : 0));
+      const uint32_t L = lvl1[gi];
+      ensure_level(g.kind == GateKind::XOR ? lvl2[gi] : L);
       if (g.kind == GateKind::XOR) {
         xor_t1[gi] = Slot{L, (uint32_t)lvl_gates[L].size()};
         lvl_gates[L].push_back(gi);      // AND(a,!b)
         lvl_gates[L].push_back(gi);      // AND(!a,b)
-        wire_slot[g.out] = Slot{L + 1, (uint32_t)lvl_gates[L + 1].size()};
-        lvl_gates[L + 1].push_back(gi);  // OR
-        c->wire_level[g.out] = L + 1;
+        wire_slot[g.out] = Slot{lvl2[gi], (uint32_t)lvl_gates[lvl2[gi]].size()};
+        lvl_gates[lvl2[gi]].push_back(gi);  // OR
       } else {
         wire_slot[g.out] = Slot{L, (uint32_t)lvl_gates[L].size()};
         lvl_gates[L].push_back(gi);
-        c->wire_level[g.out] = L;
       }
       break;
     }
@@ -241,8 +349,6 @@ static int build_plan(bfhe_circuit *c) {
   std::vector<uint32_t> first(NL, 0);
   uint32_t row = 0;
   std::vector<std::vector<uint32_t>> not_rows(NL);
-  c->max_width = 0;
-  c->n_bootstraps = 0;
   for (uint32_t L = 0; L < NL; L++) {
     const uint32_t cnt = (L == 0) ? c->n_in : (uint32_t)lvl_gates[L].size();
     const uint32_t rpr = (cnt + c->world - 1) / c->world;
@@ -251,7 +357,6 @@ static int build_plan(bfhe_circuit *c) {
     row += rpr * c->world;
     not_rows[L].resize(lvl_nots[L].size());
     for (auto &r : not_rows[L]) r = row++;
-    if (L > 0) { c->max_width = std::max(c->max_width, cnt); c->n_bootstraps += cnt; }
   }
   c->fresh_base = row;
   row += c->n_in;
@@ -550,7 +655,7 @@ extern "C" int bfhe_circuit_info(const bfhe_circuit *c, uint32_t *n_inputs, uint
   if (n_output_bits) *n_output_bits = c->nl.out_bits;
   if (n_gates) *n_gates = c->nl.n_and + c->nl.n_or + c->nl.n_xor + c->nl.n_not;
   if (n_bootstraps) *n_bootstraps = c->n_bootstraps;
-  if (n_levels) *n_levels = (uint32_t)c->levels.size() - 1;
+  if (n_levels) *n_levels = c->asap_levels;
   if (max_width) *max_width = c->max_width;
   return BFHE_OK;
 }
@@ -586,6 +691,16 @@ extern "C" int bfhe_circuit_set_sharding(bfhe_circuit *c, int rank, int world, c
     int rc = g_nccl.CommInitRank(&c->comm, world, uid, rank);
     if (rc) { set_error(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); return BFHE_ERR_NCCL; }
   }
+  if (c->loaded) {
+    free_device(c);
+    return build_plan(c);
+  }
+  return BFHE_OK;
+}
+extern "C" int bfhe_circuit_set_wave_capacity(bfhe_circuit *c, int cap) {
+  if (!c || cap < -1) return BFHE_ERR_ARG;
+  if (cap == c->wave_cap_req) return BFHE_OK;
+  c->wave_cap_req = cap;
   if (c->loaded) {
     free_device(c);
     return build_plan(c);

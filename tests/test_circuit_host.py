@@ -115,3 +115,55 @@ def test_level_partition_covers_every_gate_once(bfhe, hctx, world):
             assert all(int(x) < f for x in g["in0"]) or L == 0
     assert total == c.info()["bootstraps"]
     assert misc["total_rows"] > max(seen_rows)
+
+
+@pytest.mark.parametrize("name,cap", [("adder_2bit", 2), ("parity", 3), ("comparator_32bit_signed_lt", 5), ("mult_32x32", 148),
+                                      ("AES-non-expanded", 148)])
+def test_wave_packing_is_a_valid_schedule(bfhe, hctx, name, cap):
+    """bfhe_circuit_set_wave_capacity: every wave holds at most `cap` bootstraps (whole throughput waves of 4*cap when at least
+    8*cap gates are ready), every operand row is produced by an earlier wave, every bootstrap is placed exactly once, and the
+    ASAP statistics the reference-shaped info() reports do not change."""
+    c = load_circuit(bfhe, hctx, name)
+    info0, asap_levels = c.info(), c.plan_misc()["n_levels"] - 1
+    c.set_wave_capacity(cap)
+    assert c.info() == info0
+    misc = c.plan_misc()
+    total, produced = 0, set()
+    for L in range(misc["n_levels"]):
+        g, first, rpr = c.level_plan(L, 0, 1)
+        if L > 0:
+            assert 0 < len(g) and (len(g) <= cap or (len(g) % (4 * cap) == 0)), (L, len(g))
+            total += len(g)
+            for x in g:
+                assert int(x["in0"]) in produced and int(x["in1"]) in produced, (L, x)
+        nots = c.plan_misc(L)["nots"]
+        for row in g["out"]:
+            produced.add(int(row))
+        for a, b in nots:
+            assert int(a) in produced
+            produced.add(int(b))
+    assert total == info0["bootstraps"]
+    waves = misc["n_levels"] - 1
+    assert waves >= asap_levels and waves >= -(-info0["bootstraps"] // max(cap, 1)) // 4
+    if name == "AES-non-expanded":  # 420 ASAP levels cost ~790 one-gate-per-SM launches; packed: close to bootstraps / 148 = 556
+        assert waves <= 600, waves
+    c.set_wave_capacity(0)
+    assert c.plan_misc()["n_levels"] - 1 == asap_levels
+
+
+@pytest.mark.parametrize("name", ["adder_2bit", "parity"])
+def test_wave_packing_keeps_ciphertexts(bfhe, orc, hctx, name):
+    """Same keys, same fresh encryptions: the packed schedule produces bit-identical output ciphertexts (oracle as executor)."""
+    from helpers import oracle_run_plan
+    o = orc.Oracle(orc.TOY, orc.GINX)
+    o.keygen(5)
+    v = VECTORS[name]["vectors"][0]
+    c = load_circuit(bfhe, bfhe.Context(bfhe.TOY, bfhe.GINX, device=-1), name)
+    outs0, slab0 = oracle_run_plan(c, o, v["inputs"], seed=3)
+    rows0 = [int(r) & 0x7fffffff for r in c.plan_misc()["out_rows"]]
+    c.set_wave_capacity(2)
+    outs1, slab1 = oracle_run_plan(c, o, v["inputs"], seed=3)
+    rows1 = [int(r) & 0x7fffffff for r in c.plan_misc()["out_rows"]]
+    assert outs0 == outs1 == v["golden"]
+    for a, b in zip(rows0, rows1):
+        assert np.array_equal(slab0[a], slab1[b])

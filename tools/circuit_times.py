@@ -17,7 +17,10 @@ ctx.btkeygen(2)
 for name in names:
     c = B.Circuit(ctx)
     c.load_npz(os.path.join(ROOT, "tests", "golden", "circuits", name + ".npz"))
+    if os.environ.get("WAVE_CAP") is not None:
+        c.set_wave_capacity(int(os.environ["WAVE_CAP"]))
     info = c.info()
+    waves = c.plan_misc()["n_levels"] - 1
     best = None
     for rep, v in enumerate(V[name]["vectors"][:2]):
         c.Reset()
@@ -28,7 +31,7 @@ for name in names:
         out = c.Clock()[0]
         t2 = time.perf_counter()
         ok = out == v["golden"]
-        r = dict(circuit=name, bootstraps=info["bootstraps"], levels=info["levels"], max_width=info["max_width"],
+        r = dict(circuit=name, bootstraps=info["bootstraps"], levels=info["levels"], waves=waves, max_width=info["max_width"],
                  set_input_ms=1e3 * (t1 - t0), clock_wall_ms=1e3 * (t2 - t1), device_ms=c.stats()["device_ms"], kat_ok=ok,
                  bootstraps_per_s=info["bootstraps"] / (t2 - t1))
         if best is None or r["clock_wall_ms"] < best["clock_wall_ms"] or not ok:
