@@ -18,6 +18,7 @@
 //    IMAD.WIDE (the 64-bit-product forms appear to use the FP64 multiplier), so there is no idle pipe to move butterflies to.
 #include "common.hpp"
 #include <cuda_runtime.h>
+#include <type_traits>
 
 namespace bfhe {
 namespace v2 {
@@ -514,6 +515,289 @@ blind_rotate_v2_kernel(const __grid_constant__ DevConst P, const DevGate *__rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Latency form on a 2-CTA thread-block cluster: ONE gate on TWO SMs (narrow circuit wavefronts: fewer gates than half the
+// SMs, where the time of a level is the latency of one bootstrap -- SHA-256 / MD5, and every circuit once its levels are
+// sharded over several GPUs).  CTA r of the cluster owns accumulator component r:
+//   inverse transform of product row r -> accumulate -> its four digit transforms (two warps per digit row, one 16-value
+//   tile per thread and pass) -> cluster barrier -> external product on ITS half of the evaluation slots (rows of the
+//   other component are read from the peer CTA's shared memory over DSMEM; the peer component's product is written into
+//   the peer's row) -> cluster barrier.
+// Each CTA does exactly half of the arithmetic of a step; per step 2 cluster barriers and 8 KB read + 2 KB written over
+// DSMEM.  The CTA's half of the step's key tile (64 KB) is staged by TMA bulk copies behind an mbarrier, issued right after
+// the previous product.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(
+                   smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ u32 cluster_rank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ u32 dsmem_addr(const void *local, u32 rank) { // shared::cluster address of `local` in CTA `rank`
+  u32 a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(local)), "r"(rank));
+  return a;
+}
+__device__ __forceinline__ uint2 dsmem_ld2(u32 addr) {
+  uint2 v;
+  asm volatile("ld.shared::cluster.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dsmem_st2(u32 addr, uint2 v) { asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory"); }
+
+// forward transform of one digit by TWO warps (T = 32*h + lane), one tile per thread and pass
+__device__ __forceinline__ void ntt_forward_split(const u32 *dp, int l, u32 *buf, const DevConst &P, const Tabs &tt, int T, int bar_id, u32 Z) {
+  const u32 Q = P.Q, Q2 = P.Q2, qoff = P.Q - (1u << (LOGBG - 1));
+  u32 x[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) x[k] = ((dp[T + 64 * k] >> (LOGBG * l)) & ((1u << LOGBG) - 1)) + qoff;
+  ct_stages<8, 1, (BFHE_V2_SOL_FW & 15)>(x, P.tw, P.tws, Q, Q2, Z);
+  col_store(buf, x, T);
+  bar_sync(bar_id, 64);
+  {
+    u32 w[16], ws[16];
+    load_tw_mid(tt.fw, w, T >> 2);
+    load_tw_mid(tt.fws, ws, T >> 2);
+    mid_load(buf, x, T);
+    ct_stages<8, 2, ((BFHE_V2_SOL_FW >> 4) & 7)>(x, w, ws, Q, Q2, Z);
+    mid_store(buf, x, T);
+  }
+  bar_sync(bar_id, 64);
+  {
+    u32 w[16], ws[16];
+    load_tw_narrow(tt.fw, w, T);
+    load_tw_narrow(tt.fws, ws, T);
+    row_load(buf, x, T);
+    ct_stages<4, 1, ((BFHE_V2_SOL_FW >> 7) & 7)>(x, w, ws, Q, Q2, Z);
+    row_store(buf, x, T);
+  }
+}
+
+struct Cl2Cfg {
+  static constexpr int THREADS = 256, HALF = N / 2, KEYPOLYS = 2 * ROWS * 2;
+  static constexpr u32 KEYBYTES = (u32)KEYPOLYS * HALF * 4;
+  // words: digit rows [DG][N] | dp [N] | twiddles [4N] | F [2N] | key tile [KEYPOLYS][HALF]; then u16 idx[NPAD]; then the mbarrier
+  static constexpr size_t words = (size_t)DG * N + N + 4 * N + 2 * N + (size_t)KEYPOLYS * HALF;
+  static constexpr size_t smem_bytes = words * 4 + NPAD * 2 + 16;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cl2Cfg::THREADS, 1)
+blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count, const u32 *__restrict__ bk,
+                        const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
+  constexpr int HALF = Cl2Cfg::HALF, KEYPOLYS = Cl2Cfg::KEYPOLYS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u32 *rows = reinterpret_cast<u32 *>(smem_raw);   // [DG][N]: digit l of MY component; row 0 doubles as the product row
+  u32 *dp = rows + (size_t)DG * N;                 // centred accumulator + DIGIT_OFF, natural order
+  u32 *s_tw = dp + N;
+  u32 *s_F = s_tw + 4 * N;
+  u32 *s_key = s_F + 2 * N;                        // [sign][row][cc][HALF]: this CTA's slots of the step's two RGSW ciphertexts
+  u16 *s_idx = reinterpret_cast<u16 *>(s_key + (size_t)KEYPOLYS * HALF);
+  u64 *s_bar = reinterpret_cast<u64 *>(s_idx + NPAD);
+  __shared__ u32 s_b, s_zero;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 r = cluster_rank(), peer = r ^ 1u; // r = accumulator component this CTA owns
+  const size_t gi = blockIdx.x >> 1;
+  const u32 Q = P.Q, q = P.q, n = P.n;
+  const DevGate dg = gates[gi];
+
+  if (tid == 0) {
+    s_zero = 0;
+    mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 4 * N; i += Cl2Cfg::THREADS) s_tw[i] = g_tw[i];
+  for (int i = tid; i < 2 * N; i += Cl2Cfg::THREADS) s_F[i] = g_F[i];
+  const Tabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
+  { // LWE prep, as in the other kernels (both CTAs of the cluster compute it)
+    const u32 gate = dg.op & 0xff;
+    for (u32 i = tid; i <= n; i += Cl2Cfg::THREADS) {
+      u32 x = dg.in0[i];
+      if (dg.op & OP_NEG0) x = (i == n) ? (q / 4 + q - x) % q : (q - x) % q;
+      u32 v;
+      if (gate == OP_BOOTSTRAP) v = (i == n) ? (x + q / 4) % q : x;
+      else {
+        u32 y = dg.in1[i];
+        if (dg.op & OP_NEG1) y = (i == n) ? (q / 4 + q - y) % q : (q - y) % q;
+        v = (gate == OP_XOR_FAST || gate == OP_XNOR_FAST) ? (2 * (x + q - y)) % q : (x + y) % q;
+      }
+      if (i == n) s_b = v;
+      else s_idx[i] = (u16)(((q - v) % q) * P.factor);
+    }
+  }
+  __syncthreads();
+  const u32 Z = *(volatile u32 *)&s_zero;
+  // key copy of this kernel: [step][rank][polynomial][HALF] -- each CTA's 64 KB of a step are contiguous (four 16 KB bulk copies;
+  // 32 copies of 2 KB out of the [step][polynomial][N] layout took 2.5 us to land and stalled every step)
+  auto issue_keys = [&](u32 step) { // the LAST warp (idle while warps 0-1 run the inverse transform)
+    if (lane == 0) mbar_expect_tx(s_bar, Cl2Cfg::KEYBYTES);
+    __syncwarp();
+    const u32 *src = bk + ((size_t)step * 2 + r) * KEYPOLYS * HALF;
+    if (lane < 4) bulk_g2s(s_key + (size_t)lane * 4096, src + (size_t)lane * 4096, 16384, s_bar);
+  };
+  static_assert(Cl2Cfg::KEYBYTES == 4 * 16384, "four bulk copies");
+  if (warp == 7 && n > 0) issue_keys(0);
+  { // accumulator init: component 0 = 0, component 1 = test vector
+    u32 q1 = 0, q2 = 0, b = 0;
+    if (r == 1) {
+      const u32 gate = dg.op & 0xff;
+      q1 = P.gate_const[gate == OP_BOOTSTRAP ? OP_AND : gate];
+      q2 = (q1 + q / 2) % q;
+      b = s_b;
+    }
+    for (u32 idx = tid; idx < (u32)N; idx += Cl2Cfg::THREADS) {
+      u32 v = DIGIT_OFF;
+      if (r == 1 && idx % P.factor == 0) {
+        const u32 t = (b + q - idx / P.factor) % q;
+        const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
+        v = in ? DIGIT_OFF - P.Q8 : DIGIT_OFF + P.Q8;
+      }
+      dp[idx] = v;
+    }
+  }
+  __syncthreads();
+
+  // external product: thread t owns slots (physical words) HALF*r + 2t, +1
+  const int o = HALF * (int)r + 2 * tid;
+  u32 ex[2];
+#pragma unroll
+  for (int sl = 0; sl < 2; sl++) ex[sl] = 2 * (__brev((u32)unphys(o + sl)) >> (32 - LOGN)) + 1;
+  const u32 peer_rows = dsmem_addr(rows, peer);
+  const u32 qinv = P.qinv_neg;
+  const int T = 32 * (warp & 1) + lane; // logical thread of a two-warp transform
+
+  auto close_step = [&]() { // warps 0 and 1: inverse transform of product row 0, accumulate, publish
+    u32 x[16];
+    ntt_inverse_split<2>(x, rows, P, tt, T, 5, Z);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const u32 s = dp[T + 64 * k] + x[k];
+      dp[T + 64 * k] = (s >= DIGIT_OFF + (Q >> 1)) ? s - Q : s;
+    }
+  };
+
+#ifdef BFHE_PHASE_TIMING
+  long long tph[5] = {0, 0, 0, 0, 0}, tc0, tc1;
+  tc0 = clock64();
+#endif
+  for (u32 step = 0; step < n; step++) {
+    if (step > 0) {
+      if (warp < 2) close_step();
+      __syncthreads();
+    }
+    PH_T(0);
+    ntt_forward_split(dp, warp >> 1, rows + (size_t)(warp >> 1) * N, P, tt, T, 1 + (warp >> 1), Z);
+    PH_T(1);
+    cluster_arrive(); // my digit rows are complete ...
+    __syncthreads();  // ... and visible to the other warps of this CTA, which read them in the local half of the product
+    mbar_wait(s_bar, step & 1);
+    PH_T(2);
+    auto mac = [&](auto RC) {
+      constexpr int r = decltype(RC)::value, peer = 1 - r; // compile-time copy of the rank: keeps everything in registers
+      const u32 m = s_idx[step];
+      u32 fp[2], fn[2];
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const u32 y = m * ex[sl], ny = 0u - y;
+        fp[sl] = s_F[f_index(y)];
+        fn[sl] = s_F[f_index(ny)];
+      }
+      u64 sp[2][2] = {{0, 0}, {0, 0}}, sn[2][2] = {{0, 0}, {0, 0}}; // [cc][slot]
+      // rows of component c sit at row index c + 2l of the RGSW ciphertexts; mine first (local), ...
+#pragma unroll
+      for (int l = 0; l < DG; l++) {
+        const uint2 d = *reinterpret_cast<const uint2 *>(rows + (size_t)l * N + o);
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          const uint2 kp = *reinterpret_cast<const uint2 *>(s_key + (size_t)((0 * ROWS + 2 * l + r) * 2 + cc) * HALF + 2 * tid);
+          const uint2 kn = *reinterpret_cast<const uint2 *>(s_key + (size_t)((1 * ROWS + 2 * l + r) * 2 + cc) * HALF + 2 * tid);
+          sp[cc][0] += (u64)d.x * kp.x; sp[cc][1] += (u64)d.y * kp.y;
+          sn[cc][0] += (u64)d.x * kn.x; sn[cc][1] += (u64)d.y * kn.y;
+        }
+      }
+      cluster_wait(); // ... and the peer's once both CTAs have arrived: the barrier latency hides behind the local half
+#pragma unroll
+      for (int l = 0; l < DG; l++) {
+        const uint2 d = dsmem_ld2(peer_rows + (u32)((l * N + o) * 4));
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          const uint2 kp = *reinterpret_cast<const uint2 *>(s_key + (size_t)((0 * ROWS + 2 * l + peer) * 2 + cc) * HALF + 2 * tid);
+          const uint2 kn = *reinterpret_cast<const uint2 *>(s_key + (size_t)((1 * ROWS + 2 * l + peer) * 2 + cc) * HALF + 2 * tid);
+          sp[cc][0] += (u64)d.x * kp.x; sp[cc][1] += (u64)d.y * kp.y;
+          sn[cc][0] += (u64)d.x * kn.x; sn[cc][1] += (u64)d.y * kn.y;
+        }
+      }
+      uint2 out[2];
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) {
+        out[cc].x = redc((u64)redc(sp[cc][0], Q, qinv) * fp[0] + (u64)redc(sn[cc][0], Q, qinv) * fn[0], Q, qinv);
+        out[cc].y = redc((u64)redc(sp[cc][1], Q, qinv) * fp[1] + (u64)redc(sn[cc][1], Q, qinv) * fn[1], Q, qinv);
+      }
+      // my component's product stays here (row 0, my slots); the other component's goes into the peer's row 0 (my slots)
+      *reinterpret_cast<uint2 *>(rows + o) = out[r];
+      dsmem_st2(peer_rows + (u32)(o * 4), out[peer]);
+    };
+    if (r == 0) mac(std::integral_constant<int, 0>{});
+    else mac(std::integral_constant<int, 1>{});
+    PH_T(3);
+    cluster_sync_all(); // products exchanged; nobody reads digit rows or the key tile any more
+    PH_T(4);
+    if (warp == 7 && step + 1 < n) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy reads of the tile above, async-proxy writes below
+      issue_keys(step + 1);
+    }
+  }
+
+  // ---- epilogue: last inverse transform, sample extraction (a14) and ModSwitch Q -> qKS (a15) ----
+  if (n > 0 && warp < 2) close_step();
+  __syncthreads();
+  u32 *e = ext + gi * (N + 4);
+  const u64 qKS = P.qKS;
+  for (u32 j = tid; j < (u32)N; j += Cl2Cfg::THREADS) {
+    u32 a = dp[j] - DIGIT_OFF;
+    a += ((int)a < 0) ? Q : 0u;
+    if (acc_dbg) acc_dbg[(gi * 2 + r) * N + j] = a;
+    if (r == 0) {
+      const u32 v = (j == 0) ? a : (a == 0 ? 0 : Q - a); // Transpose: a'_0 = a_0, a'_k = -a_{N-k}
+      e[(j == 0) ? 0 : N - j] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+    } else if (j == 0) {
+      const u32 v = csub(a + P.Q8, Q);
+      e[N] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+    }
+  }
+#ifdef BFHE_PHASE_TIMING
+  if (acc_dbg && lane == 0 && (warp == 0 || warp == 7))
+    for (int i = 0; i < 5; i++) acc_dbg[(gi * 2 + r) * N + 32 + 8 * (warp == 7) + i] = (u32)(tph[i] / 1000); // kilo-cycles
+#endif
+  cluster_sync_all(); // a CTA must not exit while its peer may still touch its shared memory
+}
+
+// key copy of the cluster kernel: [step][polynomial][N] -> [step][rank][polynomial][N/2]
+__global__ void bk_split_cl2_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t nsteps) {
+  constexpr int KP = Cl2Cfg::KEYPOLYS, HALF = Cl2Cfg::HALF;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsteps * KP * N; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t step = i / ((size_t)KP * N), rem = i % ((size_t)KP * N);
+    const int pl = (int)(rem / N), o = (int)(rem % N), rk = o / HALF;
+    dst[((step * 2 + rk) * KP + pl) * HALF + (o % HALF)] = src[i];
+  }
+}
+
 // bootstrapping key: [chunk][lane][4] order of kernels.cu -> physical row order of this kernel (word phys(p) = slot p)
 __global__ void bk_permute_v2_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t npoly) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npoly * N; i += (size_t)gridDim.x * blockDim.x) {
@@ -529,7 +813,46 @@ bool v2_supported(const DevConst &P, int method_ap) {
   return !method_ap && P.N == 1024 && P.dG == 4 && P.logBG == 7 && P.Q == v2::SOLINAS_Q && P.n <= (u32)v2::NPAD;
 }
 int v2_set_attrs() {
-  return (int)cudaFuncSetAttribute(v2::blind_rotate_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cfg::smem_bytes);
+  int rc = (int)cudaFuncSetAttribute(v2::blind_rotate_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cfg::smem_bytes);
+  rc |= (int)cudaFuncSetAttribute(v2::blind_rotate_cl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cl2Cfg::smem_bytes);
+  return rc;
+}
+// how many gates the cluster form runs at once (2-CTA clusters must sit inside one GPC, so this can be less than SMs / 2)
+int cl2_max_gates() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  if (v2_set_attrs()) return cached = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * 148, 1, 1);
+  cfg.blockDim = dim3(v2::Cl2Cfg::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = v2::Cl2Cfg::smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, v2::blind_rotate_cl2_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  return cached = n;
+}
+int launch_blind_rotate_cl2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
+                            LaunchInfo *info) {
+  if (count <= 0) return 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    int rc = v2_set_attrs();
+    if (rc) return rc;
+    attr_done = true;
+  }
+  if (info) { info->gates_per_cta = 1; info->ctas = 2 * count; info->smem_bytes = v2::Cl2Cfg::smem_bytes; }
+  v2::blind_rotate_cl2_kernel<<<2 * count, v2::Cl2Cfg::THREADS, v2::Cl2Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk3, vb.d_tw2,
+                                                                                                         vb.d_F, d_ext, d_acc_dbg);
+  return (int)cudaGetLastError();
+}
+int launch_bk_split_cl2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
+  if (npoly == 0) return 0;
+  v2::bk_split_cl2_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly / v2::Cl2Cfg::KEYPOLYS);
+  return (int)cudaGetLastError();
 }
 int launch_bk_permute_v2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
   if (npoly == 0) return 0;

@@ -14,6 +14,8 @@ names = sys.argv[1:] or ["comparator_32bit_signed_lt", "adder_32bit", "mult_32x3
 ctx = B.Context(B.STD128_OPT, B.GINX, 0)
 ctx.keygen(1)
 ctx.btkeygen(2)
+if os.environ.get("GPC"):
+    ctx.dbg_set_gates_per_cta(int(os.environ["GPC"]))
 for name in names:
     c = B.Circuit(ctx)
     c.load_npz(os.path.join(ROOT, "tests", "golden", "circuits", name + ".npz"))
@@ -31,6 +33,8 @@ for name in names:
         out = c.Clock()[0]
         t2 = time.perf_counter()
         ok = out == v["golden"]
+        if not ok:
+            print("MISMATCH", name, rep, sum(int(a != b) for a, b in zip(out, v["golden"])), "of", len(out), file=sys.stderr, flush=True)
         r = dict(circuit=name, bootstraps=info["bootstraps"], levels=info["levels"], waves=waves, max_width=info["max_width"],
                  set_input_ms=1e3 * (t1 - t0), clock_wall_ms=1e3 * (t2 - t1), device_ms=c.stats()["device_ms"], kat_ok=ok,
                  bootstraps_per_s=info["bootstraps"] / (t2 - t1))

@@ -15,6 +15,12 @@ for count in [int(a) for a in os.environ.get('COUNTS', '1,148').split(',')]:
     g["op"] = B.NAND; g["in0"] = 2 * np.arange(count); g["in1"] = 2 * np.arange(count) + 1; g["out"] = 2 * count + np.arange(count)
     ctx.dbg_set_gates_per_cta(int(os.environ.get('GPC', '8')))
     acc = ctx.dbg_blind_rotate(slab, g)
+    if os.environ.get('GPC') == '32':  # cluster kernel: [gate][rank][32 + 8*(warp==7) + phase]
+        for h in (0, 1):
+            t = acc[:, :, 32 + 8 * h:37 + 8 * h].astype(np.float64)
+            names = ["intt(w0-1)+sync", "fwd split", "keywait+cluster sync", "mac", "cluster sync"]
+            print(count, "gates, warp", 7 * h, {n: round(float(v), 1) for n, v in zip(names, t.mean((0, 1)))}, "total kcyc", round(float(t.sum(2).mean()), 1))
+        continue
     if os.environ.get('GPC') == '16':  # kernels_v2.cu: [gate][component][32 + 8*h + phase]
         for h in (0, 1):
             t = acc[:, :, 32 + 8 * h:37 + 8 * h].astype(np.float64)
