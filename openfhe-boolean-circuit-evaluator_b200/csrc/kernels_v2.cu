@@ -561,8 +561,23 @@ __device__ __forceinline__ uint2 dsmem_ld2(u32 addr) {
 }
 __device__ __forceinline__ void dsmem_st2(u32 addr, uint2 v) { asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory"); }
 
+// remote store whose arrival is counted on the destination CTA's mbarrier (complete_tx): the receiver needs no cluster-scope
+// fence, it just waits for the phase of its own barrier
+__device__ __forceinline__ void st_async4(u32 dsmem, uint4 v, u32 dsmem_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dsmem), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "r"(dsmem_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async2(u32 dsmem, uint2 v, u32 dsmem_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dsmem), "r"(v.x), "r"(v.y), "r"(dsmem_bar)
+               : "memory");
+}
+
 // forward transform of one digit by TWO warps (T = 32*h + lane), one tile per thread and pass
-__device__ __forceinline__ void ntt_forward_split(const u32 *dp, int l, u32 *buf, const DevConst &P, const Tabs &tt, int T, int bar_id, u32 Z) {
+// push_dst != 0: the finished tile (16 consecutive words of the row) is not stored here but sent to the peer CTA at shared::cluster
+// address push_dst + 4 * (word offset in the row), counted on the peer's mbarrier push_bar
+__device__ __forceinline__ void ntt_forward_split(const u32 *dp, int l, u32 *buf, const DevConst &P, const Tabs &tt, int T, int bar_id, u32 Z,
+                                                  u32 push_dst = 0, u32 push_bar = 0) {
   const u32 Q = P.Q, Q2 = P.Q2, qoff = P.Q - (1u << (LOGBG - 1));
   u32 x[16];
 #pragma unroll
@@ -585,16 +600,23 @@ __device__ __forceinline__ void ntt_forward_split(const u32 *dp, int l, u32 *buf
     load_tw_narrow(tt.fws, ws, T);
     row_load(buf, x, T);
     ct_stages<4, 1, ((BFHE_V2_SOL_FW >> 7) & 7)>(x, w, ws, Q, Q2, Z);
-    row_store(buf, x, T);
+    if (push_dst == 0) row_store(buf, x, T);
+    else {
+      const int b = row_base(T);
+#pragma unroll
+      for (int c = 0; c < 4; c++) st_async4(push_dst + 4u * (u32)(b ^ (4 * c)), make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]), push_bar);
+    }
   }
 }
 
 struct Cl2Cfg {
   static constexpr int THREADS = 256, HALF = N / 2, KEYPOLYS = 2 * ROWS * 2;
   static constexpr u32 KEYBYTES = (u32)KEYPOLYS * HALF * 4;
-  // words: digit rows [DG][N] | dp [N] | twiddles [4N] | F [2N] | key tile [KEYPOLYS][HALF]; then u16 idx[NPAD]; then the mbarrier
-  static constexpr size_t words = (size_t)DG * N + N + 4 * N + 2 * N + (size_t)KEYPOLYS * HALF;
-  static constexpr size_t smem_bytes = words * 4 + NPAD * 2 + 16;
+  // words: digit rows [DG][N] | peer's digit rows, my slots [DG][HALF] | dp [N] | twiddles [4N] | F [2N] | key tile [KEYPOLYS][HALF];
+  // then u16 idx[NPAD]; then three mbarriers (key tile, peer rows, peer product)
+  static constexpr size_t words = (size_t)DG * N + (size_t)DG * HALF + N + 4 * N + 2 * N + (size_t)KEYPOLYS * HALF;
+  static constexpr size_t smem_bytes = words * 4 + NPAD * 2 + 32;
+  static constexpr u32 ROWS_TX = (u32)DG * HALF * 4, PROD_TX = (u32)HALF * 4; // bytes pushed to a CTA per step
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cl2Cfg::THREADS, 1)
@@ -602,13 +624,14 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
                         const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
   constexpr int HALF = Cl2Cfg::HALF, KEYPOLYS = Cl2Cfg::KEYPOLYS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  u32 *rows = reinterpret_cast<u32 *>(smem_raw);   // [DG][N]: digit l of MY component; row 0 doubles as the product row
-  u32 *dp = rows + (size_t)DG * N;                 // centred accumulator + DIGIT_OFF, natural order
+  u32 *rows = reinterpret_cast<u32 *>(smem_raw);   // [DG][N]: digit l of MY component (only my half of the slots is kept); row 0 doubles as the product row
+  u32 *stage = rows + (size_t)DG * N;              // [DG][HALF]: digit l of the PEER's component at my slots, pushed by the peer
+  u32 *dp = stage + (size_t)DG * HALF;             // centred accumulator + DIGIT_OFF, natural order
   u32 *s_tw = dp + N;
   u32 *s_F = s_tw + 4 * N;
   u32 *s_key = s_F + 2 * N;                        // [sign][row][cc][HALF]: this CTA's slots of the step's two RGSW ciphertexts
   u16 *s_idx = reinterpret_cast<u16 *>(s_key + (size_t)KEYPOLYS * HALF);
-  u64 *s_bar = reinterpret_cast<u64 *>(s_idx + NPAD);
+  u64 *s_bar = reinterpret_cast<u64 *>(s_idx + NPAD); // [0] key tile (TMA), [1] peer rows, [2] peer product
   __shared__ u32 s_b, s_zero;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -619,7 +642,9 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
 
   if (tid == 0) {
     s_zero = 0;
-    mbar_init(s_bar, 1);
+    mbar_init(s_bar + 0, 1);
+    mbar_init(s_bar + 1, 1);
+    mbar_init(s_bar + 2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 4 * N; i += Cl2Cfg::THREADS) s_tw[i] = g_tw[i];
@@ -671,16 +696,17 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
       dp[idx] = v;
     }
   }
-  __syncthreads();
+  cluster_sync_all(); // both CTAs' mbarriers are initialised before anything is pushed
 
   // external product: thread t owns slots (physical words) HALF*r + 2t, +1
   const int o = HALF * (int)r + 2 * tid;
   u32 ex[2];
 #pragma unroll
   for (int sl = 0; sl < 2; sl++) ex[sl] = 2 * (__brev((u32)unphys(o + sl)) >> (32 - LOGN)) + 1;
-  const u32 peer_rows = dsmem_addr(rows, peer);
+  const u32 peer_row0 = dsmem_addr(rows, peer), peer_stage = dsmem_addr(stage, peer);
+  const u32 peer_bar_rows = dsmem_addr(s_bar + 1, peer), peer_bar_prod = dsmem_addr(s_bar + 2, peer);
   const u32 qinv = P.qinv_neg;
-  const int T = 32 * (warp & 1) + lane; // logical thread of a two-warp transform
+  const int h = warp & 1, T = 32 * h + lane; // logical thread of a two-warp transform
 
   auto close_step = [&]() { // warps 0 and 1: inverse transform of product row 0, accumulate, publish
     u32 x[16];
@@ -696,18 +722,37 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   long long tph[5] = {0, 0, 0, 0, 0}, tc0, tc1;
   tc0 = clock64();
 #endif
+  // Data moves between the two CTAs as st.async pushes counted on the RECEIVER's mbarrier, so the step loop contains no
+  // cluster-scope fence (barrier.cluster.arrive.release alone cost ~1000 cycles per use here).  Order of events, CTA r:
+  //   forward transforms: tiles at my slots are stored locally, tiles at the peer's slots are pushed into the peer's stage[]
+  //   product: local rows first, then (peer-rows barrier) the staged rows; my component's result -> my row 0, the other
+  //   component's -> pushed into the peer's row 0 (those words of the peer's row are dead: the peer pushed them to me before)
+  //   inverse transform after the peer-product barrier.
+  // WAR safety: the peer overwrites stage[] for step s+1 only after it received my whole product of step s, which every one of my
+  // threads pushes after its last read of stage[]; it overwrites my row 0 only after I pushed the words it replaces.
   for (u32 step = 0; step < n; step++) {
     if (step > 0) {
-      if (warp < 2) close_step();
+      if (warp < 2) {
+        mbar_wait(s_bar + 2, (step - 1) & 1); // the peer's half of my product row has landed
+        close_step();
+      }
       __syncthreads();
     }
+    if (tid == 0) { // this step's expectations (posted after the previous phases completed; early pushes just run the count negative)
+      mbar_expect_tx(s_bar + 1, Cl2Cfg::ROWS_TX);
+      mbar_expect_tx(s_bar + 2, Cl2Cfg::PROD_TX);
+    }
     PH_T(0);
-    ntt_forward_split(dp, warp >> 1, rows + (size_t)(warp >> 1) * N, P, tt, T, 1 + (warp >> 1), Z);
+    {
+      const int l = warp >> 1;
+      const bool mine = (u32)h == r; // warp h finishes the tiles of slot half h
+      ntt_forward_split(dp, l, rows + (size_t)l * N, P, tt, T, 1 + l, Z, mine ? 0u : peer_stage + 4u * (u32)(l * HALF) - 4u * (u32)(HALF * (int)peer),
+                        peer_bar_rows);
+    }
     PH_T(1);
-    cluster_arrive(); // my digit rows are complete ...
-    __syncthreads();  // ... and visible to the other warps of this CTA, which read them in the local half of the product
-    mbar_wait(s_bar, step & 1);
+    __syncthreads(); // my halves of my digit rows are visible to all warps of this CTA
     PH_T(2);
+    mbar_wait(s_bar, step & 1);
     auto mac = [&](auto RC) {
       constexpr int r = decltype(RC)::value, peer = 1 - r; // compile-time copy of the rank: keeps everything in registers
       const u32 m = s_idx[step];
@@ -731,10 +776,10 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
           sn[cc][0] += (u64)d.x * kn.x; sn[cc][1] += (u64)d.y * kn.y;
         }
       }
-      cluster_wait(); // ... and the peer's once both CTAs have arrived: the barrier latency hides behind the local half
+      mbar_wait(s_bar + 1, step & 1); // ... then the peer's, whose push latency hides behind the local half
 #pragma unroll
       for (int l = 0; l < DG; l++) {
-        const uint2 d = dsmem_ld2(peer_rows + (u32)((l * N + o) * 4));
+        const uint2 d = *reinterpret_cast<const uint2 *>(stage + (size_t)l * HALF + 2 * tid);
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
           const uint2 kp = *reinterpret_cast<const uint2 *>(s_key + (size_t)((0 * ROWS + 2 * l + peer) * 2 + cc) * HALF + 2 * tid);
@@ -751,12 +796,12 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
       }
       // my component's product stays here (row 0, my slots); the other component's goes into the peer's row 0 (my slots)
       *reinterpret_cast<uint2 *>(rows + o) = out[r];
-      dsmem_st2(peer_rows + (u32)(o * 4), out[peer]);
+      st_async2(peer_row0 + (u32)(o * 4), out[peer], peer_bar_prod);
     };
     if (r == 0) mac(std::integral_constant<int, 0>{});
     else mac(std::integral_constant<int, 1>{});
     PH_T(3);
-    cluster_sync_all(); // products exchanged; nobody reads digit rows or the key tile any more
+    __syncthreads(); // row 0 (my half) visible to warps 0-1; nobody reads the key tile any more
     PH_T(4);
     if (warp == 7 && step + 1 < n) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy reads of the tile above, async-proxy writes below
@@ -765,7 +810,10 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   }
 
   // ---- epilogue: last inverse transform, sample extraction (a14) and ModSwitch Q -> qKS (a15) ----
-  if (n > 0 && warp < 2) close_step();
+  if (n > 0 && warp < 2) {
+    mbar_wait(s_bar + 2, (n - 1) & 1);
+    close_step();
+  }
   __syncthreads();
   u32 *e = ext + gi * (N + 4);
   const u64 qKS = P.qKS;
@@ -785,7 +833,7 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   if (acc_dbg && lane == 0 && (warp == 0 || warp == 7))
     for (int i = 0; i < 5; i++) acc_dbg[(gi * 2 + r) * N + 32 + 8 * (warp == 7) + i] = (u32)(tph[i] / 1000); // kilo-cycles
 #endif
-  cluster_sync_all(); // a CTA must not exit while its peer may still touch its shared memory
+  cluster_sync_all(); // a CTA must not exit while its peer may still push into its shared memory
 }
 
 // key copy of the cluster kernel: [step][polynomial][N] -> [step][rank][polynomial][N/2]
