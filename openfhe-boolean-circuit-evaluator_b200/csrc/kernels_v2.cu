@@ -734,6 +734,7 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     if (step > 0) {
       if (warp < 2) {
         mbar_wait(s_bar + 2, (step - 1) & 1); // the peer's half of my product row has landed
+        PH_T(4);
         close_step();
       }
       __syncthreads();

@@ -121,13 +121,52 @@ static void free_device(bfhe_circuit *c) {
 // ---------------------------------------------------------------------------------------------
 // planning
 // ---------------------------------------------------------------------------------------------
-static int build_plan(bfhe_circuit *c) {
-  const Netlist &nl = c->nl;
-  c->wave_cap = c->wave_cap_req > 0 ? (uint32_t)c->wave_cap_req : 0;
-  if (c->wave_cap_req < 0 && c->ctx && c->ctx->device >= 0) {
-    int sms = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->ctx->device) == cudaSuccess && sms > 0) c->wave_cap = (uint32_t)sms * (uint32_t)c->world;
+static int build_plan_cap(bfhe_circuit *c, uint32_t cap);
+
+// estimated evaluation time of the current plan (ms), from the measured cost of one launch per kernel form on B200:
+// cluster form (one gate on two SMs) 1.60 ms up to `cl2` gates per rank, one-gate-per-SM form 2.40 ms per wave of `sms`, four-gates-
+// per-SM form 7.6 ms per wave of 4*sms; key switch and (sharded) the all-gather ride on top
+static double plan_cost_ms(const bfhe_circuit *c, int sms, int cl2) {
+  double t = 0;
+  for (size_t L = 0; L < c->levels.size(); L++) {
+    const long n = c->level_rpr[L];
+    if (n == 0) continue;
+    double one;
+    if (n <= cl2) one = 1.60;
+    else {
+      const double lat = (double)((n + sms - 1) / sms) * 2.40, thr = (double)((n + 4 * sms - 1) / (4 * sms)) * 7.6;
+      one = lat < thr ? lat : thr;
+    }
+    t += one + (c->world > 1 ? 0.05 : 0.0);
   }
+  return t;
+}
+
+// wave_cap_req = -1 with a device attached: try the candidate wave capacities (ASAP levels, one cluster-form wave, one
+// one-gate-per-SM wave -- each times the number of ranks) and keep the cheapest plan under plan_cost_ms.  Depth-bound circuits
+// (SHA-256, MD5) end up on the cluster form, work-bound ones (AES, multipliers) on full one-gate-per-SM waves.
+static int build_plan(bfhe_circuit *c) {
+  if (c->wave_cap_req >= 0 || !c->ctx || c->ctx->device < 0) return build_plan_cap(c, c->wave_cap_req > 0 ? (uint32_t)c->wave_cap_req : 0);
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->ctx->device) != cudaSuccess || sms <= 0) return build_plan_cap(c, 0);
+  const int cl2 = (c->ctx->v2.d_tw2 && c->ctx->p.method == BFHE_GINX) ? cl2_max_gates() : 0;
+  uint32_t cands[3] = {0u, (uint32_t)sms * (uint32_t)c->world, (uint32_t)cl2 * (uint32_t)c->world};
+  uint32_t best = 0;
+  double best_t = 0;
+  for (int k = 0; k < 3; k++) {
+    if (k > 0 && cands[k] == 0) continue;
+    int rc = build_plan_cap(c, cands[k]);
+    if (rc) return rc;
+    const double t = plan_cost_ms(c, sms, cl2);
+    if (k == 0 || t < best_t) { best = cands[k]; best_t = t; }
+  }
+  return build_plan_cap(c, best);
+}
+
+static int build_plan_cap(bfhe_circuit *c, uint32_t cap) {
+  const Netlist &nl = c->nl;
+  c->wave_cap = cap;
+  c->topo.clear();
   const uint32_t NW = nl.n_wires, NG = (uint32_t)nl.gates.size();
   const uint32_t NONE = 0xffffffffu;
   std::vector<uint32_t> producer(NW, NONE);
