@@ -131,10 +131,12 @@ template <int E> __device__ __forceinline__ void load_lane_tw(const u32 *tab, u3
 #define BFHE_STREAM_TW 1
 #endif
 __device__ __forceinline__ u32 comp4(const uint4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
-template <int E, bool UNI, int SOLMASK = 0, bool STREAM = false>
+// PRE: the products of the FIRST stage arrive precomputed in pre[0 .. E/2) (digit transforms: twiddle * small digit comes
+// from a 128-entry table, see blind_rotate_kernel), x[E/2 ..) is not read.
+template <int E, bool UNI, int SOLMASK = 0, bool STREAM = false, bool PRE = false>
 __device__ __forceinline__ void ct_pass(u32 (&x)[E], const u32 *__restrict__ utw, const u32 *__restrict__ utws,
                                         const u32 (&w)[E], const u32 (&ws)[E], u32 Q, u32 Q2, const u32 *tab = nullptr,
-                                        const u32 *tabs = nullptr, int lane = 0) {
+                                        const u32 *tabs = nullptr, int lane = 0, const u32 *pre = nullptr) {
   int si = 0;
   uint4 cw = make_uint4(0, 0, 0, 0), cws = cw;
 #pragma unroll
@@ -155,7 +157,9 @@ __device__ __forceinline__ void ct_pass(u32 (&x)[E], const u32 *__restrict__ utw
 #pragma unroll
       for (int j = 0; j < t; j++) {
         const int a = gi * 2 * t + j, b = a + t;
-        u32 T = sol ? mul_shoup<true>(x[b], ww, wws, Q) : mul_shoup<false>(x[b], ww, wws, Q);
+        u32 T;
+        if (PRE && si == 0) T = pre[j];
+        else T = sol ? mul_shoup<true>(x[b], ww, wws, Q) : mul_shoup<false>(x[b], ww, wws, Q);
         x[b] = x[a] - T + Q2;
         x[a] = x[a] + T;
       }
@@ -221,12 +225,13 @@ struct TwTabs { // shared-memory per-lane twiddle tables, each N words
 
 // forward: x in column layout (index lane+32k, coefficient form, values < Q) -> row layout (index E*lane+j,
 // evaluation form, lazy < (2*logN+1)Q).  buf: N-word smem scratch, left holding garbage.
-template <int LOGN, int SOLW = 0, int SOLN = 0>
-__device__ __forceinline__ void ntt_forward(u32 (&x)[(1 << LOGN) / 32], u32 *buf, const DevConst &P, const TwTabs &tt, int lane) {
+template <int LOGN, int SOLW = 0, int SOLN = 0, bool PRE = false>
+__device__ __forceinline__ void ntt_forward(u32 (&x)[(1 << LOGN) / 32], u32 *buf, const DevConst &P, const TwTabs &tt, int lane,
+                                            const u32 *pre = nullptr) {
   constexpr int E = (1 << LOGN) / 32;
   const u32 Q = P.Q, Q2 = P.Q2;
   u32 w[E], ws[E];
-  ct_pass<E, true, SOLW>(x, P.tw, P.tws, w, ws, Q, Q2);
+  ct_pass<E, true, SOLW, false, PRE>(x, P.tw, P.tws, w, ws, Q, Q2, nullptr, nullptr, 0, pre);
   if constexpr (LOGN & 1) { // span-16 stage across lanes (lane bit 4): group index = k, twiddle psi_br[16+k]
     const bool up = lane & 16;
 #pragma unroll
@@ -304,7 +309,10 @@ template <int LOGN, int DG, int LOGBG, int G, bool AP> struct BrCfg {
   static constexpr int W = 2 * G, THREADS = 32 * W;
   static constexpr int NPAD = AP ? 1024 : 512; // per-gate index table (>= n*dR for AP, >= n for GINX)
   static constexpr size_t dct_words = (size_t)G * ROWS * N;
-  static constexpr size_t smem_bytes = (dct_words + 4 * N + (AP ? 0 : 2 * N)) * 4 + (size_t)G * NPAD * 2;
+  // first-stage product table: twiddle * (digit - B/2) mod Q for the 2^LOGBG digit values, one copy per bank (STD128_OPT shape only)
+  static constexpr bool LUT = (LOGBG == 7 && LOGN == 10 && G <= 4);
+  static constexpr size_t lut_words = LUT ? (size_t)32 << LOGBG : 0;
+  static constexpr size_t smem_bytes = (dct_words + 4 * N + (AP ? 0 : 2 * N) + lut_words) * 4 + (size_t)G * NPAD * 2;
 };
 
 template <int LOGN, int DG, int LOGBG, int G, bool AP>
@@ -319,10 +327,17 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
   u32 *dct = reinterpret_cast<u32 *>(smem_raw);                 // [G][ROWS][N]
   u32 *s_tw = dct + Cfg::dct_words;                             // fw | fws | iw | iws
   u32 *s_psiM = s_tw + 4 * N;                                   // [2N] Montgomery psi^k (GINX)
-  u16 *s_idx = reinterpret_cast<u16 *>(s_psiM + (AP ? 0 : 2 * N)); // [G][NPAD]
+  u32 *s_lut = s_psiM + (AP ? 0 : 2 * N);                       // [2^LOGBG][32] (Cfg::LUT)
+  u16 *s_idx = reinterpret_cast<u16 *>(s_lut + Cfg::lut_words); // [G][NPAD]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = warp >> 1, c = warp & 1; // this warp owns accumulator component c of gate g
+  if constexpr (Cfg::LUT) { // the first stage of every digit transform multiplies a digit in [-B/2, B/2) by the one twiddle psi^(N/2)
+    for (int i = tid; i < (int)Cfg::lut_words; i += Cfg::THREADS) {
+      const u32 d = (u32)i >> 5;
+      s_lut[i] = (u32)(((u64)P.tw[1] * ((d + P.Q - (1u << (LOGBG - 1))) % P.Q)) % P.Q);
+    }
+  }
   const int gate0 = blockIdx.x * G;
   const int gcount = min(G, count - gate0);
   const u32 Q = P.Q, q = P.q, n = P.n;
@@ -414,15 +429,18 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
       }
 #pragma unroll
       for (int l = 0; l < DG; l++) {
-        u32 x[E];
+        u32 x[E], pre[Cfg::LUT ? E / 2 : 1];
 #pragma unroll
         for (int k = 0; k < E; k++) {
           const u32 dpk = LEAN ? (((acc[k] < (Q >> 1)) ? acc[k] : acc[k] - Q) + DIGIT_OFF) : dp[LEAN ? 0 : k];
-          const u32 r = ((dpk >> (LOGBG * l)) & ((1u << LOGBG) - 1)) - (1u << (LOGBG - 1));
-          x[k] = min(r, r + Q);
+          const u32 dgt = (dpk >> (LOGBG * l)) & ((1u << LOGBG) - 1);
+          // digit - B/2 + Q: congruent to the signed digit, lazy in (Q - B/2, Q + B/2); the forward transform needs no canonical
+          // input (values then stay below (2 logN + 2) Q < 2^32)
+          if (Cfg::LUT && k >= E / 2) { pre[Cfg::LUT ? k - E / 2 : 0] = s_lut[(dgt << 5) + lane]; x[k] = 0; }
+          else x[k] = dgt + (Q - (1u << (LOGBG - 1)));
         }
         u32 *buf = dct + ((size_t)g * ROWS + c + 2 * l) * N;
-        ntt_forward<LOGN, BFHE_SOL_THR_WIDE, BFHE_SOL_THR_NARROW>(x, buf, P, tt, lane);
+        ntt_forward<LOGN, BFHE_SOL_THR_WIDE, BFHE_SOL_THR_NARROW, Cfg::LUT>(x, buf, P, tt, lane, pre);
         row_store<E>(buf, x, lane);
       }
     }
@@ -859,8 +877,7 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
       u32 x[E];
 #pragma unroll
       for (int k = 0; k < E; k++) {
-        const u32 r = ((dig[c * N + lane + 32 * k] >> (LOGBG * l)) & ((1u << LOGBG) - 1)) - (1u << (LOGBG - 1));
-        x[k] = min(r, r + Q);
+        x[k] = ((dig[c * N + lane + 32 * k] >> (LOGBG * l)) & ((1u << LOGBG) - 1)) + (Q - (1u << (LOGBG - 1))); // lazy: digit - B/2 + Q
       }
       u32 *buf = dct + (size_t)warp * N;
       ntt_forward<LOGN, BFHE_SOL_LAT_WIDE, BFHE_SOL_LAT_NARROW>(x, buf, P, tt, lane);
