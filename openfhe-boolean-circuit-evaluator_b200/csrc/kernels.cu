@@ -1074,7 +1074,7 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   // Which variant?  latency form: one gate per CTA, one wave of `sms` gates takes ~2.3 ms (STD128_OPT GINX);
   // throughput form: 4 gates per CTA share every key word, one wave of 4*sms gates takes ~7.6 ms.  Pick the cheaper
   // estimate (measured on B200, profiles/r1_*): narrow circuit levels go to the latency form, wide batches to the other.
-  // narrower than the number of co-resident 2-CTA clusters: one gate on two SMs (1.87 ms per wave instead of 2.33 ms)
+  // narrower than the number of co-resident 2-CTA clusters: one gate on two SMs (1.49 ms per wave instead of 2.30 ms)
   if (force_g == 0 && have_v2 && v2->d_bk3 && count <= cl2_max_gates())
     return launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   const long lat_cost = (long)((count + sms - 1) / sms) * 23;

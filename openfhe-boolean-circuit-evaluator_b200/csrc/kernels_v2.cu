@@ -561,6 +561,100 @@ __device__ __forceinline__ uint2 dsmem_ld2(u32 addr) {
 }
 __device__ __forceinline__ void dsmem_st2(u32 addr, uint2 v) { asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory"); }
 
+// ---- inverse transform on 8-value tiles by FOUR warps (T = 0..127): three register stages per pass, the widest stage (span 512)
+// across lanes 16 apart.  Same row layout; used by the cluster kernel, where the inverse transform of the one product row is the
+// serial part of a step.  On return x[k] = coefficient T6 + 64*(k + 8*hi), fully reduced (T6 = 16*warp + lane % 16, hi = lane / 16).
+template <int T, int TEND, int B, int MAXOUT> struct Gs8 {
+  static constexpr int NB = 2 * B;
+  static constexpr bool LAST = (T == TEND);
+  static constexpr bool RED = LAST ? (NB > MAXOUT) : (NB > 16);
+  static constexpr int OUTB = RED ? 2 : NB;
+  __device__ __forceinline__ static void run(u32 (&x)[8], const u32 *__restrict__ w, const u32 *__restrict__ ws, u32 Q, u32 Z) {
+    static_assert(B <= 16, "GS input bound too large");
+    const u32 off = B * Q;
+    u32 D[4], hi[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int gi = i / T, a = gi * 2 * T + (i % T), b = a + T;
+      D[i] = x[a] - x[b] + off;
+      const u32 S = add3(x[a], x[b], Z);
+      x[a] = RED ? lazy_reduce(S, Q) : S;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) hi[i] = __umulhi(D[i], ws[8 / (2 * T) + i / T]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int gi = i / T, b = gi * 2 * T + (i % T) + T;
+      x[b] = D[i] * w[8 / (2 * T) + gi] - hi[i] * Q;
+    }
+    if constexpr (!LAST) Gs8<2 * T, TEND, OUTB, MAXOUT>::run(x, w, ws, Q, Z);
+  }
+};
+__host__ __device__ constexpr int gs8_bound(int B) { // three stages, sums pulled back when they would pass 16Q going in
+  for (int s = 0; s < 3; s++) B = (2 * B > 16) ? 2 : 2 * B;
+  return B;
+}
+template <int B0> __device__ __forceinline__ void ntt_inverse_quad8(u32 (&x)[8], u32 *buf, const DevConst &P, const Tabs &tt, int T, int bar_id, u32 Z) {
+  const u32 Q = P.Q;
+  u32 w[8], ws[8];
+  { // narrow pass: positions 8*T + j, stages with 512, 256, 128 groups
+    const int T3 = T >> 1, hb = T & 1, b = row_base(T3);
+    const uint4 a0 = *reinterpret_cast<const uint4 *>(buf + (b ^ (8 * hb))), a1 = *reinterpret_cast<const uint4 *>(buf + (b ^ (8 * hb + 4)));
+    x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w; x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
+    const uint4 t4 = *reinterpret_cast<const uint4 *>(tt.iw + 512 + 256 * hb + 4 * T3), t4s = *reinterpret_cast<const uint4 *>(tt.iws + 512 + 256 * hb + 4 * T3);
+    const uint2 t2 = *reinterpret_cast<const uint2 *>(tt.iw + 256 + 2 * T), t2s = *reinterpret_cast<const uint2 *>(tt.iws + 256 + 2 * T);
+    w[4] = t4.x; w[5] = t4.y; w[6] = t4.z; w[7] = t4.w; ws[4] = t4s.x; ws[5] = t4s.y; ws[6] = t4s.z; ws[7] = t4s.w;
+    w[2] = t2.x; w[3] = t2.y; ws[2] = t2s.x; ws[3] = t2s.y;
+    w[1] = tt.iw[128 + T]; ws[1] = tt.iws[128 + T];
+    Gs8<1, 4, B0, 16>::run(x, w, ws, Q, Z);
+    *reinterpret_cast<uint4 *>(buf + (b ^ (8 * hb))) = make_uint4(x[0], x[1], x[2], x[3]);
+    *reinterpret_cast<uint4 *>(buf + (b ^ (8 * hb + 4))) = make_uint4(x[4], x[5], x[6], x[7]);
+  }
+  constexpr int B1 = gs8_bound(B0);
+  bar_sync(bar_id, 128);
+  { // middle pass: positions 64u + 8r + v, stages with 64, 32, 16 groups
+    const int u = T >> 3, v = T & 7;
+    const int b = 64 * u + 16 * ((u >> 1) & 1) + 8 * (u & 1) + v; // mid_base with w = v >> 1, plus the low bit of v
+    const uint4 t4 = *reinterpret_cast<const uint4 *>(tt.iw + 64 + 4 * u), t4s = *reinterpret_cast<const uint4 *>(tt.iws + 64 + 4 * u);
+    const uint2 t2 = *reinterpret_cast<const uint2 *>(tt.iw + 32 + 2 * u), t2s = *reinterpret_cast<const uint2 *>(tt.iws + 32 + 2 * u);
+    w[4] = t4.x; w[5] = t4.y; w[6] = t4.z; w[7] = t4.w; ws[4] = t4s.x; ws[5] = t4s.y; ws[6] = t4s.z; ws[7] = t4s.w;
+    w[2] = t2.x; w[3] = t2.y; ws[2] = t2s.x; ws[3] = t2s.y;
+    w[1] = tt.iw[16 + u]; ws[1] = tt.iws[16 + u];
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = buf[b ^ mid_k(r)];
+    Gs8<1, 4, B1, 16>::run(x, w, ws, Q, Z);
+#pragma unroll
+    for (int r = 0; r < 8; r++) buf[b ^ mid_k(r)] = x[r];
+  }
+  constexpr int B2 = gs8_bound(B1);
+  bar_sync(bar_id, 128);
+  { // wide pass: positions T6 + 64*(k + 8*hi); stages with 8, 4, 2 groups in registers, the last one across lanes
+    const int lane = T & 31, hi = lane >> 4, T6 = 16 * (T >> 5) + (lane & 15);
+    const int cb = col_base(T6);
+    const u32 *a0 = buf + cb, *a1 = buf + (cb ^ 8), *a2 = buf + (cb ^ 16), *a3 = buf + (cb ^ 24);
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = ((k & 3) == 0 ? a0 : (k & 3) == 1 ? a1 : (k & 3) == 2 ? a2 : a3)[64 * (k + 8 * hi)];
+#pragma unroll
+    for (int g = 0; g < 4; g++) { w[4 + g] = tt.iw[8 + 4 * hi + g]; ws[4 + g] = tt.iws[8 + 4 * hi + g]; }
+#pragma unroll
+    for (int g = 0; g < 2; g++) { w[2 + g] = tt.iw[4 + 2 * hi + g]; ws[2 + g] = tt.iws[4 + 2 * hi + g]; }
+    w[1] = tt.iw[2 + hi]; ws[1] = tt.iws[2 + hi];
+    Gs8<1, 4, B2, 16>::run(x, w, ws, Q, Z);
+    constexpr int B3 = gs8_bound(B2);
+    static_assert(B3 <= 16, "bound");
+    const u32 w1 = tt.iw[1], w1s = tt.iws[1], off = B3 * Q;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const u32 o = __shfl_xor_sync(0xffffffffu, x[k], 16);
+      const u32 D = o - x[k] + off; // upper lane: (lower - upper) * w
+      const u32 m = D * w1 - __umulhi(D, w1s) * Q;
+      x[k] = hi ? m : x[k] + o;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = csub(lazy_reduce(x[k], Q), Q);
+  }
+}
+
 // remote store whose arrival is counted on the destination CTA's mbarrier (complete_tx): the receiver needs no cluster-scope
 // fence, it just waits for the phase of its own barrier
 __device__ __forceinline__ void st_async4(u32 dsmem, uint4 v, u32 dsmem_bar) {
@@ -708,13 +802,15 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   const u32 qinv = P.qinv_neg;
   const int h = warp & 1, T = 32 * h + lane; // logical thread of a two-warp transform
 
-  auto close_step = [&]() { // warps 0 and 1: inverse transform of product row 0, accumulate, publish
-    u32 x[16];
-    ntt_inverse_split<2>(x, rows, P, tt, T, 5, Z);
+  auto close_step = [&]() { // warps 0-3: inverse transform of product row 0 (8-value tiles), accumulate, publish
+    u32 x[8];
+    ntt_inverse_quad8<2>(x, rows, P, tt, tid, 5, Z);
+    const int hi = lane >> 4, T6 = 16 * warp + (lane & 15);
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-      const u32 s = dp[T + 64 * k] + x[k];
-      dp[T + 64 * k] = (s >= DIGIT_OFF + (Q >> 1)) ? s - Q : s;
+    for (int k = 0; k < 8; k++) {
+      const int j = T6 + 64 * (k + 8 * hi);
+      const u32 s = dp[j] + x[k];
+      dp[j] = (s >= DIGIT_OFF + (Q >> 1)) ? s - Q : s;
     }
   };
 
@@ -732,7 +828,7 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   // threads pushes after its last read of stage[]; it overwrites my row 0 only after I pushed the words it replaces.
   for (u32 step = 0; step < n; step++) {
     if (step > 0) {
-      if (warp < 2) {
+      if (warp < 4) {
         mbar_wait(s_bar + 2, (step - 1) & 1); // the peer's half of my product row has landed
         PH_T(4);
         close_step();
@@ -811,7 +907,7 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   }
 
   // ---- epilogue: last inverse transform, sample extraction (a14) and ModSwitch Q -> qKS (a15) ----
-  if (n > 0 && warp < 2) {
+  if (n > 0 && warp < 4) {
     mbar_wait(s_bar + 2, (n - 1) & 1);
     close_step();
   }

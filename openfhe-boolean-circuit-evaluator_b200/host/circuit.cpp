@@ -124,7 +124,7 @@ static void free_device(bfhe_circuit *c) {
 static int build_plan_cap(bfhe_circuit *c, uint32_t cap);
 
 // estimated evaluation time of the current plan (ms), from the measured cost of one launch per kernel form on B200:
-// cluster form (one gate on two SMs) 1.60 ms up to `cl2` gates per rank, one-gate-per-SM form 2.40 ms per wave of `sms`, four-gates-
+// cluster form (one gate on two SMs) 1.55 ms up to `cl2` gates per rank, one-gate-per-SM form 2.36 ms per wave of `sms`, four-gates-
 // per-SM form 7.6 ms per wave of 4*sms; key switch and (sharded) the all-gather ride on top
 static double plan_cost_ms(const bfhe_circuit *c, int sms, int cl2) {
   double t = 0;
@@ -132,9 +132,9 @@ static double plan_cost_ms(const bfhe_circuit *c, int sms, int cl2) {
     const long n = c->level_rpr[L];
     if (n == 0) continue;
     double one;
-    if (n <= cl2) one = 1.60;
+    if (n <= cl2) one = 1.55;
     else {
-      const double lat = (double)((n + sms - 1) / sms) * 2.40, thr = (double)((n + 4 * sms - 1) / (4 * sms)) * 7.6;
+      const double lat = (double)((n + sms - 1) / sms) * 2.36, thr = (double)((n + 4 * sms - 1) / (4 * sms)) * 7.6;
       one = lat < thr ? lat : thr;
     }
     t += one + (c->world > 1 ? 0.05 : 0.0);
