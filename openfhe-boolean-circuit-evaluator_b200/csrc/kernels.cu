@@ -130,6 +130,9 @@ template <int E> __device__ __forceinline__ void load_lane_tw(const u32 *tab, u3
 #ifndef BFHE_STREAM_TW
 #define BFHE_STREAM_TW 1
 #endif
+#ifndef BFHE_PAIRED_DIGITS
+#define BFHE_PAIRED_DIGITS 1
+#endif
 __device__ __forceinline__ u32 comp4(const uint4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 // PRE: the products of the FIRST stage arrive precomputed in pre[0 .. E/2) (digit transforms: twiddle * small digit comes
 // from a 128-entry table, see blind_rotate_kernel), x[E/2 ..) is not read.
@@ -252,6 +255,27 @@ __device__ __forceinline__ void ntt_forward(u32 (&x)[(1 << LOGN) / 32], u32 *buf
     load_lane_tw<E>(tt.fws, ws, lane);
     ct_pass<E, false, SOLN>(x, P.tw, P.tws, w, ws, Q, Q2);
   }
+}
+
+// two forward transforms at once (two digit polynomials of the same accumulator component): twice the independent butterflies
+// per stage for the scheduler, which with two warps per scheduler is what a transform lacks to keep the FMA-heavy pipe busy
+template <int LOGN, int SOLW = 0, int SOLN = 0, bool PRE = false>
+__device__ __forceinline__ void ntt_forward2(u32 (&xa)[(1 << LOGN) / 32], u32 (&xb)[(1 << LOGN) / 32], u32 *bufa, u32 *bufb, const DevConst &P,
+                                             const TwTabs &tt, int lane, const u32 *prea = nullptr, const u32 *preb = nullptr) {
+  constexpr int E = (1 << LOGN) / 32;
+  static_assert((LOGN & 1) == 0, "even log2 N only");
+  const u32 Q = P.Q, Q2 = P.Q2;
+  u32 w[E], ws[E];
+  ct_pass<E, true, SOLW, false, PRE>(xa, P.tw, P.tws, w, ws, Q, Q2, nullptr, nullptr, 0, prea);
+  ct_pass<E, true, SOLW, false, PRE>(xb, P.tw, P.tws, w, ws, Q, Q2, nullptr, nullptr, 0, preb);
+  __syncwarp();
+  col_store<E>(bufa, xa, lane);
+  col_store<E>(bufb, xb, lane);
+  __syncwarp();
+  row_load<E>(bufa, xa, lane);
+  row_load<E>(bufb, xb, lane);
+  ct_pass<E, false, SOLN, true>(xa, P.tw, P.tws, w, ws, Q, Q2, tt.fw, tt.fws, lane);
+  ct_pass<E, false, SOLN, true>(xb, P.tw, P.tws, w, ws, Q, Q2, tt.fw, tt.fws, lane);
 }
 
 // inverse (unscaled: N * true value; the keys carry N^-1): x in row layout (evaluation form, values < B0*Q)
@@ -405,6 +429,12 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
   constexpr int GS = LEAN ? G / 2 : ((W >= C) ? (W / C) : 1);
   const u32 eA = 2 * brev(lane, 5) + 1; // lane part of the evaluation-point exponent 2*br(idx)+1
 
+#ifdef BFHE_PHASE_TIMING
+  long long tpt[5] = {0, 0, 0, 0, 0}, tq0 = clock64(), tq1;
+#define PT_T(i) do { tq1 = clock64(); tpt[i] += tq1 - tq0; tq0 = tq1; } while (0)
+#else
+#define PT_T(i)
+#endif
   for (int step = 0; step < nsteps; step++) {
     // ================= phase A: one warp per (gate, component) =================
     bool active = gvalid;
@@ -427,6 +457,30 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
 #pragma unroll
         for (int k = 0; k < E; k++) dp[k] = ((acc[k] < (Q >> 1)) ? acc[k] : acc[k] - Q) + DIGIT_OFF;
       }
+      // two digits per pass (STD128_OPT shape): +8 % at two gates per CTA (71.3k -> 77.0k gates/s), nothing at four (79.3k vs 79.7k),
+      // where the phase is already within ~20 % of its pipe bound (tools/phase_timing.py) -- used for G <= 2 only
+      constexpr bool PAIRED = Cfg::LUT && !LEAN && (DG % 2 == 0) && G <= 2 && BFHE_PAIRED_DIGITS;
+      if constexpr (PAIRED) {
+#pragma unroll
+        for (int l = 0; l < DG; l += 2) {
+          u32 xa[E], xb[E], prea[E / 2], preb[E / 2];
+#pragma unroll
+          for (int k = 0; k < E; k++) {
+            const u32 sh = dp[k] >> (LOGBG * l), da = sh & ((1u << LOGBG) - 1), db = (sh >> LOGBG) & ((1u << LOGBG) - 1);
+            if (k >= E / 2) {
+              prea[k - E / 2] = s_lut[(da << 5) + lane]; xa[k] = 0;
+              preb[k - E / 2] = s_lut[(db << 5) + lane]; xb[k] = 0;
+            } else {
+              xa[k] = da + (Q - (1u << (LOGBG - 1)));
+              xb[k] = db + (Q - (1u << (LOGBG - 1)));
+            }
+          }
+          u32 *bufa = dct + ((size_t)g * ROWS + c + 2 * l) * N, *bufb = bufa + 2 * N;
+          ntt_forward2<LOGN, BFHE_SOL_THR_WIDE, BFHE_SOL_THR_NARROW, true>(xa, xb, bufa, bufb, P, tt, lane, prea, preb);
+          row_store<E>(bufa, xa, lane);
+          row_store<E>(bufb, xb, lane);
+        }
+      } else {
 #pragma unroll
       for (int l = 0; l < DG; l++) {
         u32 x[E], pre[Cfg::LUT ? E / 2 : 1];
@@ -443,8 +497,10 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
         ntt_forward<LOGN, BFHE_SOL_THR_WIDE, BFHE_SOL_THR_NARROW, Cfg::LUT>(x, buf, P, tt, lane, pre);
         row_store<E>(buf, x, lane);
       }
+      }
     }
     pending = pending || active;
+    PT_T(0);
     // GINX: this warp's first key chunk is requested BEFORE the barrier, so the L2 round trip overlaps the wait for
     // the slower warps of the CTA instead of stalling the external product (ncu r1: 6 % of samples sat on these loads)
     uint4 kr[AP ? 1 : 2][ROWS][LEAN ? 1 : 2];
@@ -459,6 +515,7 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
             kr[s][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((s * ROWS + r) * 2 + cc) * N));
     }
     __syncthreads();
+    PT_T(1);
 
     // ================= phase B: external product, slot-parallel over the CTA =================
     if constexpr (LEAN) {
@@ -594,7 +651,9 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
       }
     }
     }
+    PT_T(2);
     __syncthreads();
+    PT_T(3);
   }
 
   // ---- epilogue: last inverse transform, sample extraction (a14) and ModSwitch Q -> qKS (a15) ----
@@ -625,6 +684,10 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
       const u32 v = csub(acc[0] + P.Q8, Q);
       e[N] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
     }
+#ifdef BFHE_PHASE_TIMING
+    if (acc_dbg && lane == 0)
+      for (int i = 0; i < 5; i++) acc_dbg[(gi * 2 + c) * N + 32 + i] = (u32)(tpt[i] / 1000); // kilo-cycles
+#endif
   }
 }
 

@@ -15,6 +15,12 @@ for count in [int(a) for a in os.environ.get('COUNTS', '1,148').split(',')]:
     g["op"] = B.NAND; g["in0"] = 2 * np.arange(count); g["in1"] = 2 * np.arange(count) + 1; g["out"] = 2 * count + np.arange(count)
     ctx.dbg_set_gates_per_cta(int(os.environ.get('GPC', '8')))
     acc = ctx.dbg_blind_rotate(slab, g)
+    if os.environ.get('GPC') in ('1', '2', '4'):  # first-generation throughput kernel: [gate][component][32 + phase]
+        t = acc[:, :, 32:37].astype(np.float64)
+        names = ["intt+decompose+4 ntt", "keyload+barrier1", "mac", "barrier2", "-"]
+        for w in (0, 1):
+            print(count, "gates, comp", w, {n: round(float(v), 1) for n, v in zip(names, t[:, w].mean(0))}, "total kcyc", round(float(t[:, w].sum(1).mean()), 1))
+        continue
     if os.environ.get('GPC') == '32':  # cluster kernel: [gate][rank][32 + 8*(warp==7) + phase]
         for h in (0, 1):
             t = acc[:, :, 32 + 8 * h:37 + 8 * h].astype(np.float64)
