@@ -21,6 +21,7 @@
 //    bootstrapping-key word loaded from L2 is reused G times from registers (GINX).
 #include "common.hpp"
 #include <algorithm>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace bfhe {
@@ -694,68 +695,90 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
 
 
 // ------------------------------------------------------------------------------------------
-// inverse transform spread over 4 warps (N = 1024): every lane holds 8 values instead of 32, so the serial chain
-// per thread is 4x shorter; the two widest stages of each pass run across lanes with warp shuffles
-// (lane ^ 1, lane ^ 2).  Used by the latency kernel, where only two polynomials need an INTT per step and all
-// eight warps would otherwise wait for two of them.  Warp q4 of the group handles rows (pass A) / columns (pass B)
-// 8*q4 .. 8*q4+7; lane = 4*(row or column within the warp) + s, s = which quarter of the 32 points.
+// inverse transform spread over 4 warps (N = 1024) for the latency kernel, where only two polynomials need an inverse transform per
+// step: THREE passes of three register stages on 8-value tiles, only the widest stage (span 512) across lanes (36 + 8 multiplies per
+// thread; a first version with two passes and four cross-lane stages did 24 + 32).  nat / nats: inverse twiddles
+// in natural order m + i (group i of the stage with m groups), the 512-group stage de-interleaved (groups 8t + j at
+// 512 + 256 (j >> 2) + 4t + (j & 3)) -- built in shared memory by the latency kernel.  T = 0..127 within the polynomial's 4 warps;
+// on return x[k] = coefficient T6 + 64 (k + 8 hi), T6 = 16 (T >> 5) + (T & 15), hi = (T >> 4) & 1.
 // ------------------------------------------------------------------------------------------
-template <int B> __device__ __forceinline__ void gs_shuffle_stage(u32 (&x)[8], int mask, bool up, u32 w, u32 ws, u32 Q) {
-  static_assert(B <= 16, "bound");
-  const u32 off = B * Q;
+template <int T, int B> struct Gs8Stage { // one Gentleman-Sande stage on 8 registers, half-size T; B = input bound in units of Q
+  static constexpr bool RED = (2 * B > 16);
+  static constexpr int OUTB = RED ? 2 : 2 * B;
+  __device__ __forceinline__ static void run(u32 (&x)[8], const u32 (&w)[8], const u32 (&ws)[8], u32 Q, u32 mu) {
+    static_assert(B <= 16, "bound");
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const u32 o = __shfl_xor_sync(0xffffffffu, x[j], mask);
-    const u32 D = o - x[j] + off;          // upper lane: U - V (U arrives from the lower lane)
-    x[j] = up ? mul_shoup(D, w, ws, Q) : (x[j] + o);
+    for (int i = 0; i < 4; i++) {
+      const int gi = i / T, a = gi * 2 * T + (i % T), b = a + T, p = 4 / T + gi;
+      const u32 S = x[a] + x[b], D = x[a] - x[b] + B * Q;
+      x[b] = mul_shoup(D, w[p], ws[p], Q);
+      x[a] = RED ? lazy_reduce(S, Q, mu) : S;
+    }
   }
-}
-template <int B0>
-__device__ __forceinline__ void ntt_inverse_quad(u32 (&x)[8], u32 *buf, const DevConst &P, const TwTabs &tt, const u32 *s_uitw,
-                                                 int q4, int lane, int bar_id) {
-  constexpr int E = 32;
+};
+template <int B0> __device__ __forceinline__ void ntt_inverse_quad8(u32 (&x)[8], u32 *buf, const DevConst &P, const u32 *nat, const u32 *nats, int T,
+                                                                   int bar_id) {
   const u32 Q = P.Q, mu = P.mu;
-  const int r8 = lane >> 2, s = lane & 3, line = 8 * q4 + r8;
-  u32 wl[8], wsl[8];
-  // ---- pass A: row `line`, points j = 8s .. 8s+7 (spans 1, 2, 4 in registers; 8, 16 across lanes) ----
-  {
-    const uint4 a = *reinterpret_cast<const uint4 *>(buf + Lay<E>::chunk_off(line, 2 * s));
-    const uint4 b = *reinterpret_cast<const uint4 *>(buf + Lay<E>::chunk_off(line, 2 * s + 1));
-    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  u32 w[8], ws[8];
+  auto run3 = [&](auto BC) { // three stages, returns nothing; bounds advance at compile time
+    constexpr int B = decltype(BC)::value;
+    using S1 = Gs8Stage<1, B>; using S2 = Gs8Stage<2, S1::OUTB>; using S3 = Gs8Stage<4, S2::OUTB>;
+    S1::run(x, w, ws, Q, mu); S2::run(x, w, ws, Q, mu); S3::run(x, w, ws, Q, mu);
+  };
+  constexpr int B1 = Gs8Stage<4, Gs8Stage<2, Gs8Stage<1, B0>::OUTB>::OUTB>::OUTB;
+  constexpr int B2 = Gs8Stage<4, Gs8Stage<2, Gs8Stage<1, B1>::OUTB>::OUTB>::OUTB;
+  constexpr int B3 = Gs8Stage<4, Gs8Stage<2, Gs8Stage<1, B2>::OUTB>::OUTB>::OUTB;
+  { // narrow pass: positions 8T + j (row T >> 2 of the row layout, chunks 2 (T & 3) and + 1)
+    const int tp = T >> 2, c0 = 2 * (T & 3), T3 = T >> 1, hb = T & 1;
+    u32 *p0 = buf + Lay<32>::chunk_off(tp, c0), *p1 = buf + Lay<32>::chunk_off(tp, c0 + 1);
+    const uint4 a0 = *reinterpret_cast<const uint4 *>(p0), a1 = *reinterpret_cast<const uint4 *>(p1);
+    x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w; x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
+    const uint4 t4 = *reinterpret_cast<const uint4 *>(nat + 512 + 256 * hb + 4 * T3), t4s = *reinterpret_cast<const uint4 *>(nats + 512 + 256 * hb + 4 * T3);
+    const uint2 t2 = *reinterpret_cast<const uint2 *>(nat + 256 + 2 * T), t2s = *reinterpret_cast<const uint2 *>(nats + 256 + 2 * T);
+    w[4] = t4.x; w[5] = t4.y; w[6] = t4.z; w[7] = t4.w; ws[4] = t4s.x; ws[5] = t4s.y; ws[6] = t4s.z; ws[7] = t4s.w;
+    w[2] = t2.x; w[3] = t2.y; ws[2] = t2s.x; ws[3] = t2s.y;
+    w[1] = nat[128 + T]; ws[1] = nats[128 + T];
+    run3(std::integral_constant<int, B0>{});
+    *reinterpret_cast<uint4 *>(p0) = make_uint4(x[0], x[1], x[2], x[3]);
+    *reinterpret_cast<uint4 *>(p1) = make_uint4(x[4], x[5], x[6], x[7]);
   }
-  auto ld = [&](const u32 *tab, int chunk) { return reinterpret_cast<const uint4 *>(tab)[chunk * 32 + line]; };
-  const uint4 c0 = ld(tt.iw, 0), c0s = ld(tt.iws, 0), c1 = ld(tt.iw, 1), c1s = ld(tt.iws, 1);
-  const uint4 c2 = ld(tt.iw, 2 + (s >> 1)), c2s = ld(tt.iws, 2 + (s >> 1)), c4 = ld(tt.iw, 4 + s), c4s = ld(tt.iws, 4 + s);
-  wl[4] = c4.x; wl[5] = c4.y; wl[6] = c4.z; wl[7] = c4.w;      // span 1: twiddle 16 + 4s + g
-  wsl[4] = c4s.x; wsl[5] = c4s.y; wsl[6] = c4s.z; wsl[7] = c4s.w;
-  wl[2] = (s & 1) ? c2.z : c2.x; wl[3] = (s & 1) ? c2.w : c2.y; // span 2: twiddle 8 + 2s + g
-  wsl[2] = (s & 1) ? c2s.z : c2s.x; wsl[3] = (s & 1) ? c2s.w : c2s.y;
-  wl[1] = s == 0 ? c1.x : s == 1 ? c1.y : s == 2 ? c1.z : c1.w;   // span 4: twiddle 4 + s
-  wsl[1] = s == 0 ? c1s.x : s == 1 ? c1s.y : s == 2 ? c1s.z : c1s.w;
-  wl[0] = wsl[0] = 0;
-  GsRun<8, 1, B0, false, 16>::run(x, nullptr, nullptr, wl, wsl, Q, mu);
-  constexpr int BA = gs_out_bound(8, B0, 16);
-  gs_shuffle_stage<BA>(x, 1, s & 1, (s >> 1) ? c0.w : c0.z, (s >> 1) ? c0s.w : c0s.z, Q); // span 8: twiddle 2 + (s>>1)
-  gs_shuffle_stage<2 * BA>(x, 2, s & 2, c0.y, c0s.y, Q);                                   // span 16: twiddle 1
-  constexpr int BA3 = 4 * BA;
-  *reinterpret_cast<uint4 *>(buf + Lay<E>::chunk_off(line, 2 * s)) = make_uint4(x[0], x[1], x[2], x[3]);
-  *reinterpret_cast<uint4 *>(buf + Lay<E>::chunk_off(line, 2 * s + 1)) = make_uint4(x[4], x[5], x[6], x[7]);
   asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-  // ---- pass B: column `line`, points k = 8s .. 8s+7 (index line + 32k; spans 32, 64, 128 in registers; 256, 512 across lanes) ----
+  { // middle pass: positions 64u + 8r + v
+    const int u = T >> 3, v = T & 7;
+    const int b = 64 * u + 8 * (u & 3) + 4 * (v >> 2) + (v & 3); // address of r = 0; r flips bits: 32 (r >> 2) + 8 (r & 3) + 4 (r >> 2)
+    const uint4 t4 = *reinterpret_cast<const uint4 *>(nat + 64 + 4 * u), t4s = *reinterpret_cast<const uint4 *>(nats + 64 + 4 * u);
+    const uint2 t2 = *reinterpret_cast<const uint2 *>(nat + 32 + 2 * u), t2s = *reinterpret_cast<const uint2 *>(nats + 32 + 2 * u);
+    w[4] = t4.x; w[5] = t4.y; w[6] = t4.z; w[7] = t4.w; ws[4] = t4s.x; ws[5] = t4s.y; ws[6] = t4s.z; ws[7] = t4s.w;
+    w[2] = t2.x; w[3] = t2.y; ws[2] = t2s.x; ws[3] = t2s.y;
+    w[1] = nat[16 + u]; ws[1] = nats[16 + u];
 #pragma unroll
-  for (int kk = 0; kk < 8; kk++) x[kk] = buf[Lay<E>::elem_off(8 * s + kk, line)];
+    for (int r = 0; r < 8; r++) x[r] = buf[b ^ (32 * (r >> 2) + 8 * (r & 3) + 4 * (r >> 2))];
+    run3(std::integral_constant<int, B1>{});
 #pragma unroll
-  for (int g = 0; g < 4; g++) { wl[4 + g] = s_uitw[16 + 4 * s + g]; wsl[4 + g] = s_uitw[32 + 16 + 4 * s + g]; }
+    for (int r = 0; r < 8; r++) buf[b ^ (32 * (r >> 2) + 8 * (r & 3) + 4 * (r >> 2))] = x[r];
+  }
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+  { // wide pass: positions T6 + 64 (k + 8 hi); the last stage across lanes 16 apart
+    const int lane = T & 31, hi = lane >> 4, T6 = 16 * (T >> 5) + (lane & 15), l5 = T6 & 31, t5 = T6 >> 5;
 #pragma unroll
-  for (int g = 0; g < 2; g++) { wl[2 + g] = s_uitw[8 + 2 * s + g]; wsl[2 + g] = s_uitw[32 + 8 + 2 * s + g]; }
-  wl[1] = s_uitw[4 + s]; wsl[1] = s_uitw[32 + 4 + s];
-  GsRun<8, 1, BA3, false, 16>::run(x, nullptr, nullptr, wl, wsl, Q, mu);
-  constexpr int BB = gs_out_bound(8, BA3, 16);
-  gs_shuffle_stage<BB>(x, 1, s & 1, s_uitw[2 + (s >> 1)], s_uitw[32 + 2 + (s >> 1)], Q);
-  gs_shuffle_stage<(2 * BB > 16 ? 16 : 2 * BB)>(x, 2, s & 2, s_uitw[1], s_uitw[33], Q);
-  static_assert(2 * BB <= 16, "bound");
+    for (int k = 0; k < 8; k++) x[k] = buf[32 * t5 + 64 * (k + 8 * hi) + 4 * ((l5 >> 2) ^ (t5 + 2 * (k & 3))) + (l5 & 3)];
 #pragma unroll
-  for (int kk = 0; kk < 8; kk++) x[kk] = csub(lazy_reduce(x[kk], Q, mu), Q);
+    for (int g = 0; g < 4; g++) { w[4 + g] = nat[8 + 4 * hi + g]; ws[4 + g] = nats[8 + 4 * hi + g]; }
+#pragma unroll
+    for (int g = 0; g < 2; g++) { w[2 + g] = nat[4 + 2 * hi + g]; ws[2 + g] = nats[4 + 2 * hi + g]; }
+    w[1] = nat[2 + hi]; ws[1] = nats[2 + hi];
+    run3(std::integral_constant<int, B2>{});
+    static_assert(B3 <= 16, "bound");
+    const u32 w1 = nat[1], w1s = nats[1];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const u32 o = __shfl_xor_sync(0xffffffffu, x[k], 16);
+      const u32 m = mul_shoup(o - x[k] + B3 * Q, w1, w1s, Q); // upper lane: (lower - upper) * w
+      x[k] = hi ? m : x[k] + o;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = csub(lazy_reduce(x[k], Q, mu), Q);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -792,7 +815,9 @@ template <int LOGN, int DG, int LOGBG, bool AP> struct LatCfg {
   static constexpr int NPAD = 1024;
   static constexpr int KEYPOLYS = AP ? ROWS * 2 : 2 * ROWS * 2;
   // words: dct | digits | key tile | twiddles | psi powers ; then u16 idx + u16 active list ; then the mbarrier
-  static constexpr size_t words = (size_t)ROWS * N + 2 * N + (size_t)KEYPOLYS * N + 4 * N + (AP ? 0 : 2 * N);
+  static constexpr bool QUAD = (LOGN == 10 && W == 8); // inverse transform spread over 4 warps per polynomial
+  static constexpr size_t nat_words = QUAD ? 2 * N : 0; // inverse twiddles in natural order (w | w') for ntt_inverse_quad8
+  static constexpr size_t words = (size_t)ROWS * N + 2 * N + (size_t)KEYPOLYS * N + 4 * N + (AP ? 0 : 2 * N) + nat_words;
   static constexpr size_t smem_bytes = words * 4 + 2 * NPAD * 2 + 16;
 };
 
@@ -810,12 +835,12 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   u32 *s_key = dig + 2 * N;                             // [KEYPOLYS][N] this step's key tile
   u32 *s_tw = s_key + (size_t)KEYPOLYS * N;             // fw | fws | iw | iws
   u32 *s_psiM = s_tw + 4 * N;                           // [2N] (GINX)
-  u16 *s_idx = reinterpret_cast<u16 *>(s_psiM + (AP ? 0 : 2 * N)); // [NPAD] monomial exponent / AP digit per step
+  u32 *s_nat = s_psiM + (AP ? 0 : 2 * N);               // [2N] inverse twiddles, natural order (QUAD)
+  u16 *s_idx = reinterpret_cast<u16 *>(s_nat + Cfg::nat_words); // [NPAD] monomial exponent / AP digit per step
   u16 *s_list = s_idx + NPAD;                           // [NPAD] steps that do work
   u64 *s_bar = reinterpret_cast<u64 *>(s_list + NPAD);
   __shared__ u32 s_b, s_nact;
-  __shared__ u32 s_uitw[64]; // uniform inverse twiddles (itw | itws) for lane-dependent lookups of the 4-warp INTT
-  constexpr bool QUAD = (LOGN == 10 && W == 8); // INTT spread over 4 warps per polynomial
+  constexpr bool QUAD = Cfg::QUAD;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = warp & 1, l = warp >> 1; // this warp transforms digit l of accumulator component c (row c + 2l)
@@ -827,7 +852,20 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   if (!AP)
     for (int i = tid; i < 2 * N; i += Cfg::THREADS) s_psiM[i] = g_psiM[i];
   const TwTabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
-  if (tid < 32) { s_uitw[tid] = P.itw[tid]; s_uitw[32 + tid] = P.itws[tid]; }
+  if constexpr (QUAD) { // natural-order copy of the inverse twiddles: entry k < 32 from the kernel parameters, the rest out of the
+                        // per-lane tables ([chunk][lane][4]: entry pp of lane L is twiddle groups * (32 + L) + gi)
+    auto nat_slot = [&](int k) { return k < N / 2 ? k : N / 2 + (N / 4) * (((k - N / 2) & 7) >> 2) + 4 * ((k - N / 2) >> 3) + ((k - N / 2) & 3); };
+    for (int k = tid; k < 32; k += Cfg::THREADS) { s_nat[nat_slot(k)] = P.itw[k]; s_nat[N + nat_slot(k)] = P.itws[k]; }
+    for (int i = tid; i < 32 * E; i += Cfg::THREADS) {
+      const int L = i / E, pp = i % E;
+      if (pp == 0) continue;
+      int groups = 1;
+      while (groups * 2 <= pp) groups *= 2;
+      const int k = groups * (32 + L) + (pp - groups), off = ((pp / 4) * 32 + L) * 4 + (pp % 4);
+      s_nat[nat_slot(k)] = g_twl[2 * N + off];
+      s_nat[N + nat_slot(k)] = g_twl[3 * N + off];
+    }
+  }
   if (tid == 0) {
     mbar_init(s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -880,7 +918,8 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
 
   // accumulator (coefficient form).  QUAD: 8 coefficients per thread, component qc = warp / 4, index qL + 32 * (8 * qs + kk);
   // otherwise 32 coefficients per lane in warps 0 and 1 (component = warp, index lane + 32k).
-  const int qc = warp >> 2, q4 = warp & 3, qL = 8 * q4 + (lane >> 2), qs = lane & 3;
+  const int qc = warp >> 2, q4 = warp & 3;
+  auto qpos = [&](int k) { return 16 * q4 + (lane & 15) + 64 * (k + 8 * (lane >> 4)); }; // ntt_inverse_quad8's output positions
   u32 acc[QUAD ? 8 : E];
 #pragma unroll
   for (int k = 0; k < (QUAD ? 8 : E); k++) acc[k] = 0;
@@ -890,7 +929,7 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     const u32 b = s_b, Q8 = P.Q8, Q8n = Q - P.Q8;
 #pragma unroll
     for (int k = 0; k < (QUAD ? 8 : E); k++) {
-      const u32 idx = QUAD ? (u32)(qL + 32 * (8 * qs + k)) : (u32)(lane + 32 * k);
+      const u32 idx = QUAD ? (u32)qpos(k) : (u32)(lane + 32 * k);
       if (idx % P.factor == 0) {
         const u32 t = (b + q - idx / P.factor) % q;
         const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
@@ -913,12 +952,12 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     if constexpr (QUAD) {
       if (j > 0) {
         u32 x[8];
-        ntt_inverse_quad<AP ? 8 : 4>(x, dct + (size_t)qc * N, P, tt, s_uitw, q4, lane, 1 + qc);
+        ntt_inverse_quad8<AP ? 8 : 4>(x, dct + (size_t)qc * N, P, s_nat, s_nat + N, 32 * q4 + lane, 1 + qc);
 #pragma unroll
         for (int k = 0; k < 8; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
       }
 #pragma unroll
-      for (int k = 0; k < 8; k++) dig[qc * N + qL + 32 * (8 * qs + k)] = ((acc[k] < (Q >> 1)) ? acc[k] : acc[k] - Q) + DIGIT_OFF;
+      for (int k = 0; k < 8; k++) dig[qc * N + qpos(k)] = ((acc[k] < (Q >> 1)) ? acc[k] : acc[k] - Q) + DIGIT_OFF;
     } else if (warp < 2) {
       if (j > 0) {
         u32 x[E];
@@ -1013,13 +1052,13 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   if constexpr (QUAD) {
     if (nact > 0) {
       u32 x[8];
-      ntt_inverse_quad<AP ? 8 : 4>(x, dct + (size_t)qc * N, P, tt, s_uitw, q4, lane, 1 + qc);
+      ntt_inverse_quad8<AP ? 8 : 4>(x, dct + (size_t)qc * N, P, s_nat, s_nat + N, 32 * q4 + lane, 1 + qc);
 #pragma unroll
       for (int k = 0; k < 8; k++) acc[k] = AP ? x[k] : csub(acc[k] + x[k], Q);
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const u32 jj = qL + 32 * (8 * qs + k);
+      const u32 jj = (u32)qpos(k);
       if (acc_dbg) acc_dbg[(gi * 2 + qc) * N + jj] = acc[k];
       if (qc == 0) {
         const u32 v = (jj == 0) ? acc[k] : (acc[k] == 0 ? 0 : Q - acc[k]); // a'_0 = a_0, a'_k = -a_{N-k}
