@@ -53,13 +53,14 @@ struct LaunchInfo { // filled by the launch helpers for the profiler hooks
 struct V2Bufs {
   const u32 *d_bk2 = nullptr; // bootstrapping key, rows in the kernel's physical slot order
   const u32 *d_bk3 = nullptr; // the same, split [step][cluster rank][polynomial][N/2] for the 2-CTA cluster kernel
+  const u32 *d_bk4 = nullptr; // the same, split [step][cluster rank][polynomial][N/4] for the 4-CTA cluster kernel
   const u32 *d_tw2 = nullptr; // fwd w | fwd ws | inv w | inv ws, each N words (order: kernels_v2.cu Tabs)
   const u32 *d_F = nullptr;   // (psi^k - 1) * 2^32 mod Q, k < 2N
 };
 
 // kernels.cu entry points (all asynchronous on `stream`; return cudaError_t as int)
 // force_gates_per_cta: 0 = cost model; 1, 2, 4 = first-generation throughput form; 8 = latency form; 16 = second-generation
-// throughput form; 32 = cluster latency form (one gate on two SMs)
+// throughput form; 32 = cluster latency form (one gate on two SMs); 64 = one gate on four SMs
 int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates, int count, const u32 *d_bk,
                         const u32 *d_twl /*fwd w | fwd ws | inv w | inv ws, each N words*/, const u32 *d_psiM,
                         u32 *d_ext /*count * (N+4)*/, u32 *d_acc_dbg /*nullable: count*2*N*/, int force_gates_per_cta,
@@ -69,6 +70,11 @@ bool v2_supported(const DevConst &P, int method_ap);
 int v2_set_attrs();
 int launch_bk_permute_v2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
 int cl2_max_gates(); // gates the cluster form can run concurrently on this device (0 = unavailable)
+int cl4_max_gates();
+int cl4_fast_gates(); // up to this many gates the 4-CTA form beats the 2-CTA form
+int launch_bk_split_cl4(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
+int launch_blind_rotate_cl4(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
+                            void *stream, LaunchInfo *info);
 int launch_bk_split_cl2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
 int launch_blind_rotate_v2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
                            void *stream, LaunchInfo *info);

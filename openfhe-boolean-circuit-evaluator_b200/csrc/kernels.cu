@@ -1168,8 +1168,9 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   if (count <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const bool have_v2 = v2 && v2->d_bk2 && v2_supported(P, method_ap);
-  if ((force_g == 16 || force_g == 32) && !have_v2) return (int)cudaErrorInvalidValue;
+  if ((force_g == 16 || force_g == 32 || force_g == 64) && !have_v2) return (int)cudaErrorInvalidValue;
   if (force_g == 32) return launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
+  if (force_g == 64) return launch_blind_rotate_cl4(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1177,6 +1178,8 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   // throughput form: 4 gates per CTA share every key word, one wave of 4*sms gates takes ~7.6 ms.  Pick the cheaper
   // estimate (measured on B200, profiles/r1_*): narrow circuit levels go to the latency form, wide batches to the other.
   // narrower than the number of co-resident 2-CTA clusters: one gate on two SMs (1.49 ms per wave instead of 2.30 ms)
+  if (force_g == 0 && have_v2 && v2->d_bk4 && count <= cl4_fast_gates()) // one gate on four SMs (1.19 - 1.26 ms per wave)
+    return launch_blind_rotate_cl4(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   if (force_g == 0 && have_v2 && v2->d_bk3 && count <= cl2_max_gates())
     return launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   const long lat_cost = (long)((count + sms - 1) / sms) * 23;

@@ -933,6 +933,218 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   cluster_sync_all(); // a CTA must not exit while its peer may still push into its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// ONE gate on FOUR SMs (4-CTA cluster) for wavefronts of at most a quarter of the SMs.  Rank r: component c = r & 1, half s = r >> 1.
+//   * both CTAs of a component keep the accumulator and run the inverse transform of its product row (redundantly: it is the
+//     serial part of a step and costs nothing extra in time);
+//   * CTA (c, s) transforms digits 2s and 2s + 1 of component c (two warps per row) and pushes every finished 16-word tile to the
+//     CTA that owns its quarter of the evaluation slots (possibly itself) -- st.async counted on the receiver's mbarrier;
+//   * every CTA multiplies its quarter of the slots against its quarter of the step's key tile (32 KB, TMA) and pushes the two
+//     product components to the two CTAs of each component.
+// Same write-after-read argument as the 2-CTA form: a receiver's buffers are overwritten only by pushes that causally follow the
+// last read of the previous contents (rows(s+1) follow the owner's inverse transform, which needed every CTA's product(s)).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_async1(u32 dsmem, u32 v, u32 dsmem_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dsmem), "r"(v), "r"(dsmem_bar) : "memory");
+}
+struct Cl4Cfg {
+  static constexpr int THREADS = 256, QUARTER = N / 4, KEYPOLYS = 2 * ROWS * 2;
+  static constexpr u32 KEYBYTES = (u32)KEYPOLYS * QUARTER * 4;
+  // words: all 8 digit rows at my slots [ROWS][QUARTER] | transform scratch [2][N] | product row [N] | dp [N] | twiddles [4N] | F [2N] |
+  // key tile [KEYPOLYS][QUARTER]; then u16 idx[NPAD]; then three mbarriers (key tile, digit rows, product)
+  static constexpr size_t words = (size_t)ROWS * QUARTER + 2 * N + N + N + 4 * N + 2 * N + (size_t)KEYPOLYS * QUARTER;
+  static constexpr size_t smem_bytes = words * 4 + NPAD * 2 + 32;
+  static constexpr u32 ROWS_TX = (u32)ROWS * QUARTER * 4, PROD_TX = (u32)N * 4; // bytes pushed to a CTA per step (own pushes included)
+};
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(Cl4Cfg::THREADS, 1)
+blind_rotate_cl4_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count, const u32 *__restrict__ bk,
+                        const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
+  constexpr int QUARTER = Cl4Cfg::QUARTER, KEYPOLYS = Cl4Cfg::KEYPOLYS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u32 *stage = reinterpret_cast<u32 *>(smem_raw);  // [ROWS][QUARTER]: row c + 2l of the digit transforms at MY quarter of the slots
+  u32 *frow = stage + (size_t)ROWS * QUARTER;      // [2][N]: in-place scratch of my two digit transforms
+  u32 *prow = frow + 2 * N;                        // [N]: product row of my component, pushed by all four CTAs
+  u32 *dp = prow + N;                              // centred accumulator + DIGIT_OFF, natural order
+  u32 *s_tw = dp + N;
+  u32 *s_F = s_tw + 4 * N;
+  u32 *s_key = s_F + 2 * N;                        // [sign][row][cc][QUARTER]
+  u16 *s_idx = reinterpret_cast<u16 *>(s_key + (size_t)KEYPOLYS * QUARTER);
+  u64 *s_bar = reinterpret_cast<u64 *>(s_idx + NPAD); // [0] key tile (TMA), [1] digit rows, [2] product row
+  __shared__ u32 s_b, s_zero;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 r = cluster_rank(), c = r & 1u, sub = r >> 1;
+  const size_t gi = blockIdx.x >> 2;
+  const u32 Q = P.Q, q = P.q, n = P.n;
+  const DevGate dg = gates[gi];
+
+  if (tid == 0) {
+    s_zero = 0;
+    mbar_init(s_bar + 0, 1);
+    mbar_init(s_bar + 1, 1);
+    mbar_init(s_bar + 2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 4 * N; i += Cl4Cfg::THREADS) s_tw[i] = g_tw[i];
+  for (int i = tid; i < 2 * N; i += Cl4Cfg::THREADS) s_F[i] = g_F[i];
+  const Tabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
+  { // LWE prep, as in the other kernels (all four CTAs compute it)
+    const u32 gate = dg.op & 0xff;
+    for (u32 i = tid; i <= n; i += Cl4Cfg::THREADS) {
+      u32 x = dg.in0[i];
+      if (dg.op & OP_NEG0) x = (i == n) ? (q / 4 + q - x) % q : (q - x) % q;
+      u32 v;
+      if (gate == OP_BOOTSTRAP) v = (i == n) ? (x + q / 4) % q : x;
+      else {
+        u32 y = dg.in1[i];
+        if (dg.op & OP_NEG1) y = (i == n) ? (q / 4 + q - y) % q : (q - y) % q;
+        v = (gate == OP_XOR_FAST || gate == OP_XNOR_FAST) ? (2 * (x + q - y)) % q : (x + y) % q;
+      }
+      if (i == n) s_b = v;
+      else s_idx[i] = (u16)(((q - v) % q) * P.factor);
+    }
+  }
+  __syncthreads();
+  const u32 Z = *(volatile u32 *)&s_zero;
+  auto issue_keys = [&](u32 step) { // key copy of this kernel: [step][rank][polynomial][QUARTER]: 32 KB contiguous per CTA and step
+    if (lane == 0) mbar_expect_tx(s_bar, Cl4Cfg::KEYBYTES);
+    __syncwarp();
+    const u32 *src = bk + ((size_t)step * 4 + r) * KEYPOLYS * QUARTER;
+    if (lane < 2) bulk_g2s(s_key + (size_t)lane * 4096, src + (size_t)lane * 4096, 16384, s_bar);
+  };
+  static_assert(Cl4Cfg::KEYBYTES == 2 * 16384, "two bulk copies");
+  if (warp == 7 && n > 0) issue_keys(0);
+  { // accumulator init: component 0 = 0, component 1 = test vector
+    u32 q1 = 0, q2 = 0, b = 0;
+    if (c == 1) {
+      const u32 gate = dg.op & 0xff;
+      q1 = P.gate_const[gate == OP_BOOTSTRAP ? OP_AND : gate];
+      q2 = (q1 + q / 2) % q;
+      b = s_b;
+    }
+    for (u32 idx = tid; idx < (u32)N; idx += Cl4Cfg::THREADS) {
+      u32 v = DIGIT_OFF;
+      if (c == 1 && idx % P.factor == 0) {
+        const u32 t = (b + q - idx / P.factor) % q;
+        const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
+        v = in ? DIGIT_OFF - P.Q8 : DIGIT_OFF + P.Q8;
+      }
+      dp[idx] = v;
+    }
+  }
+  cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
+
+  // external product: thread t owns slot (physical word) QUARTER * r + t
+  const int o = QUARTER * (int)r + tid;
+  const u32 ex = 2 * (__brev((u32)unphys(o)) >> (32 - LOGN)) + 1;
+  // product pushes: the four lanes of a slot group (4 consecutive slots) each serve ONE destination CTA with one 16-byte push
+  // (per-slot 4-byte pushes to four destinations quadrupled the packet count and cost 0.4 ms per wave once every SM was busy)
+  const u32 dest = (u32)lane & 3u;
+  const u32 prow_dst = dsmem_addr(prow + (o & ~3), dest), prod_bar = dsmem_addr(s_bar + 2, dest);
+  const u32 qinv = P.qinv_neg;
+  // digit transforms: warps 0-1 row 0 (digit 2 sub), warps 2-3 row 1 (digit 2 sub + 1); tile T goes to the CTA owning its quarter
+  const int h = warp & 1, T = 32 * h + lane, frj = (warp >> 1) & 1, l_mine = 2 * (int)sub + frj, R_mine = (int)c + 2 * l_mine;
+  const u32 kq = (u32)(T ^ ((T >> 3) & 1)) >> 4; // quarter (= destination rank) of tile T
+  const u32 push_dst = dsmem_addr(stage, kq) + 4u * (u32)(R_mine * QUARTER) - 4u * (u32)QUARTER * kq, push_bar = dsmem_addr(s_bar + 1, kq);
+
+  auto close_step = [&]() { // warps 0-3: inverse transform of my component's product row, accumulate, publish
+    u32 x[8];
+    ntt_inverse_quad8<2>(x, prow, P, tt, tid, 5, Z);
+    const int hi = lane >> 4, T6 = 16 * warp + (lane & 15);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int j = T6 + 64 * (k + 8 * hi);
+      const u32 s = dp[j] + x[k];
+      dp[j] = (s >= DIGIT_OFF + (Q >> 1)) ? s - Q : s;
+    }
+  };
+
+  for (u32 step = 0; step < n; step++) {
+    if (step > 0) {
+      if (warp < 4) {
+        mbar_wait(s_bar + 2, (step - 1) & 1); // all four quarters of my product row have landed
+        close_step();
+      }
+      __syncthreads();
+    }
+    if (tid == 0) { // this step's expectations (early pushes just run the count negative)
+      mbar_expect_tx(s_bar + 1, Cl4Cfg::ROWS_TX);
+      mbar_expect_tx(s_bar + 2, Cl4Cfg::PROD_TX);
+    }
+    if (warp < 4) ntt_forward_split(dp, l_mine, frow + (size_t)frj * N, P, tt, T, 1 + frj, Z, push_dst, push_bar);
+    mbar_wait(s_bar, step & 1);
+    mbar_wait(s_bar + 1, step & 1); // all eight digit rows at my slots
+    {
+      const u32 m = s_idx[step];
+      const u32 y = m * ex, ny = 0u - y;
+      const u32 fp = s_F[f_index(y)], fn = s_F[f_index(ny)];
+      u64 sp[2] = {0, 0}, sn[2] = {0, 0}; // [cc]
+#pragma unroll
+      for (int rw = 0; rw < ROWS; rw++) {
+        const u32 d = stage[rw * QUARTER + tid];
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          sp[cc] += (u64)d * s_key[(size_t)((0 * ROWS + rw) * 2 + cc) * QUARTER + tid];
+          sn[cc] += (u64)d * s_key[(size_t)((1 * ROWS + rw) * 2 + cc) * QUARTER + tid];
+        }
+      }
+      u32 out[2];
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) out[cc] = redc((u64)redc(sp[cc], Q, qinv) * fp + (u64)redc(sn[cc], Q, qinv) * fn, Q, qinv);
+      uint4 v; // component dest & 1 (it lives in ranks dest & 1 and (dest & 1) + 2) of the group's four slots
+      const int g0 = lane & ~3;
+      {
+        const u32 a0 = __shfl_sync(0xffffffffu, out[0], g0), a1 = __shfl_sync(0xffffffffu, out[0], g0 + 1);
+        const u32 a2 = __shfl_sync(0xffffffffu, out[0], g0 + 2), a3 = __shfl_sync(0xffffffffu, out[0], g0 + 3);
+        const u32 b0 = __shfl_sync(0xffffffffu, out[1], g0), b1 = __shfl_sync(0xffffffffu, out[1], g0 + 1);
+        const u32 b2 = __shfl_sync(0xffffffffu, out[1], g0 + 2), b3 = __shfl_sync(0xffffffffu, out[1], g0 + 3);
+        v = (dest & 1u) ? make_uint4(b0, b1, b2, b3) : make_uint4(a0, a1, a2, a3);
+      }
+      st_async4(prow_dst, v, prod_bar);
+    }
+    __syncthreads(); // nobody reads the key tile any more
+    if (warp == 7 && step + 1 < n) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue_keys(step + 1);
+    }
+  }
+
+  // ---- epilogue: last inverse transform, sample extraction (a14) and ModSwitch Q -> qKS (a15); ranks 0 and 1 write the result ----
+  if (n > 0 && warp < 4) {
+    mbar_wait(s_bar + 2, (n - 1) & 1);
+    close_step();
+  }
+  __syncthreads();
+  if (sub == 0) {
+    u32 *e = ext + gi * (N + 4);
+    const u64 qKS = P.qKS;
+    for (u32 j = tid; j < (u32)N; j += Cl4Cfg::THREADS) {
+      u32 a = dp[j] - DIGIT_OFF;
+      a += ((int)a < 0) ? Q : 0u;
+      if (acc_dbg) acc_dbg[(gi * 2 + c) * N + j] = a;
+      if (c == 0) {
+        const u32 v = (j == 0) ? a : (a == 0 ? 0 : Q - a); // Transpose: a'_0 = a_0, a'_k = -a_{N-k}
+        e[(j == 0) ? 0 : N - j] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+      } else if (j == 0) {
+        const u32 v = csub(a + P.Q8, Q);
+        e[N] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
+      }
+    }
+  }
+  cluster_sync_all(); // a CTA must not exit while its peers may still push into its shared memory
+}
+
+// key copy of the 4-CTA kernel: [step][polynomial][N] -> [step][rank][polynomial][N/4]
+__global__ void bk_split_cl4_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t nsteps) {
+  constexpr int KP = Cl4Cfg::KEYPOLYS, QUARTER = Cl4Cfg::QUARTER;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsteps * KP * N; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t step = i / ((size_t)KP * N), rem = i % ((size_t)KP * N);
+    const int pl = (int)(rem / N), o = (int)(rem % N), rk = o / QUARTER;
+    dst[((step * 4 + rk) * KP + pl) * QUARTER + (o % QUARTER)] = src[i];
+  }
+}
+
 // key copy of the cluster kernel: [step][polynomial][N] -> [step][rank][polynomial][N/2]
 __global__ void bk_split_cl2_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t nsteps) {
   constexpr int KP = Cl2Cfg::KEYPOLYS, HALF = Cl2Cfg::HALF;
@@ -960,7 +1172,50 @@ bool v2_supported(const DevConst &P, int method_ap) {
 int v2_set_attrs() {
   int rc = (int)cudaFuncSetAttribute(v2::blind_rotate_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cfg::smem_bytes);
   rc |= (int)cudaFuncSetAttribute(v2::blind_rotate_cl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cl2Cfg::smem_bytes);
+  rc |= (int)cudaFuncSetAttribute(v2::blind_rotate_cl4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cl4Cfg::smem_bytes);
   return rc;
+}
+template <typename K> static int max_active_clusters(K kern, int cluster, int threads, size_t smem) {
+  if (v2_set_attrs()) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster * 148, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  return n;
+}
+int cl4_max_gates() {
+  static int cached = -1;
+  if (cached < 0) cached = max_active_clusters(v2::blind_rotate_cl4_kernel, 4, v2::Cl4Cfg::THREADS, v2::Cl4Cfg::smem_bytes);
+  return cached;
+}
+// The 4-CTA form slows down when (almost) every SM carries a cluster: measured on B200 1.19 ms up to 30 gates, 1.26 ms for 31-33,
+// 1.59 ms for 34-37 (37 = co-resident maximum) -- above ~7/8 of the maximum the 2-CTA form (1.49 ms up to 74 gates) is the better one.
+int cl4_fast_gates() { const int m = cl4_max_gates(); return m - m / 8; }
+int launch_bk_split_cl4(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
+  if (npoly == 0) return 0;
+  v2::bk_split_cl4_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly / v2::Cl4Cfg::KEYPOLYS);
+  return (int)cudaGetLastError();
+}
+int launch_blind_rotate_cl4(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
+                            LaunchInfo *info) {
+  if (count <= 0) return 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    int rc = v2_set_attrs();
+    if (rc) return rc;
+    attr_done = true;
+  }
+  if (info) { info->gates_per_cta = 1; info->ctas = 4 * count; info->smem_bytes = v2::Cl4Cfg::smem_bytes; }
+  v2::blind_rotate_cl4_kernel<<<4 * count, v2::Cl4Cfg::THREADS, v2::Cl4Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk4, vb.d_tw2,
+                                                                                                         vb.d_F, d_ext, d_acc_dbg);
+  return (int)cudaGetLastError();
 }
 // how many gates the cluster form runs at once (2-CTA clusters must sit inside one GPC, so this can be less than SMs / 2)
 int cl2_max_gates() {

@@ -124,15 +124,16 @@ static void free_device(bfhe_circuit *c) {
 static int build_plan_cap(bfhe_circuit *c, uint32_t cap);
 
 // estimated evaluation time of the current plan (ms), from the measured cost of one launch per kernel form on B200:
-// cluster form (one gate on two SMs) 1.55 ms up to `cl2` gates per rank, one-gate-per-SM form 2.36 ms per wave of `sms`, four-gates-
+// 4-CTA cluster form 1.30 ms up to `cl4` gates per rank, 2-CTA cluster form 1.55 ms up to `cl2`, one-gate-per-SM form 2.36 ms per wave of `sms`, four-gates-
 // per-SM form 7.6 ms per wave of 4*sms; key switch and (sharded) the all-gather ride on top
-static double plan_cost_ms(const bfhe_circuit *c, int sms, int cl2) {
+static double plan_cost_ms(const bfhe_circuit *c, int sms, int cl2, int cl4) {
   double t = 0;
   for (size_t L = 0; L < c->levels.size(); L++) {
     const long n = c->level_rpr[L];
     if (n == 0) continue;
     double one;
-    if (n <= cl2) one = 1.55;
+    if (n <= cl4) one = 1.30;
+    else if (n <= cl2) one = 1.55;
     else {
       const double lat = (double)((n + sms - 1) / sms) * 2.36, thr = (double)((n + 4 * sms - 1) / (4 * sms)) * 7.6;
       one = lat < thr ? lat : thr;
@@ -142,22 +143,23 @@ static double plan_cost_ms(const bfhe_circuit *c, int sms, int cl2) {
   return t;
 }
 
-// wave_cap_req = -1 with a device attached: try the candidate wave capacities (ASAP levels, one cluster-form wave, one
+// wave_cap_req = -1 with a device attached: try the candidate wave capacities (ASAP levels, one 4-CTA or 2-CTA cluster-form wave, one
 // one-gate-per-SM wave -- each times the number of ranks) and keep the cheapest plan under plan_cost_ms.  Depth-bound circuits
 // (SHA-256, MD5) end up on the cluster form, work-bound ones (AES, multipliers) on full one-gate-per-SM waves.
 static int build_plan(bfhe_circuit *c) {
   if (c->wave_cap_req >= 0 || !c->ctx || c->ctx->device < 0) return build_plan_cap(c, c->wave_cap_req > 0 ? (uint32_t)c->wave_cap_req : 0);
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->ctx->device) != cudaSuccess || sms <= 0) return build_plan_cap(c, 0);
-  const int cl2 = (c->ctx->v2.d_tw2 && c->ctx->p.method == BFHE_GINX) ? cl2_max_gates() : 0;
-  uint32_t cands[3] = {0u, (uint32_t)sms * (uint32_t)c->world, (uint32_t)cl2 * (uint32_t)c->world};
+  const bool clusters = c->ctx->v2.d_tw2 && c->ctx->p.method == BFHE_GINX;
+  const int cl2 = clusters ? cl2_max_gates() : 0, cl4 = clusters ? cl4_fast_gates() : 0;
+  uint32_t cands[4] = {0u, (uint32_t)sms * (uint32_t)c->world, (uint32_t)cl2 * (uint32_t)c->world, (uint32_t)cl4 * (uint32_t)c->world};
   uint32_t best = 0;
   double best_t = 0;
-  for (int k = 0; k < 3; k++) {
+  for (int k = 0; k < 4; k++) {
     if (k > 0 && cands[k] == 0) continue;
     int rc = build_plan_cap(c, cands[k]);
     if (rc) return rc;
-    const double t = plan_cost_ms(c, sms, cl2);
+    const double t = plan_cost_ms(c, sms, cl2, cl4);
     if (k == 0 || t < best_t) { best = cands[k]; best_t = t; }
   }
   return build_plan_cap(c, best);
