@@ -52,8 +52,7 @@ struct LaunchInfo { // filled by the launch helpers for the profiler hooks
 // device buffers of the second-generation throughput kernel (kernels_v2.cu); all null when the parameter set is not covered
 struct V2Bufs {
   const u32 *d_bk2 = nullptr; // bootstrapping key, rows in the kernel's physical slot order
-  const u32 *d_bk3 = nullptr; // the same, split [step][cluster rank][polynomial][N/2] for the 2-CTA cluster kernel
-  const u32 *d_bk4 = nullptr; // the same, split [step][cluster rank][polynomial][N/4] for the 4-CTA cluster kernel
+  const u32 *d_bk4 = nullptr; // the same, split [step][quarter of the slots][polynomial][N/4]: the 2-CTA and 4-CTA cluster kernels
   const u32 *d_tw2 = nullptr; // fwd w | fwd ws | inv w | inv ws, each N words (order: kernels_v2.cu Tabs)
   const u32 *d_F = nullptr;   // (psi^k - 1) * 2^32 mod Q, k < 2N
 };
@@ -75,7 +74,6 @@ int cl4_fast_gates(); // up to this many gates the 4-CTA form beats the 2-CTA fo
 int launch_bk_split_cl4(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
 int launch_blind_rotate_cl4(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
                             void *stream, LaunchInfo *info);
-int launch_bk_split_cl2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
 int launch_blind_rotate_v2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
                            void *stream, LaunchInfo *info);
 // one gate on a 2-CTA cluster (two SMs): the latency form for wavefronts narrower than half the SM count

@@ -189,7 +189,7 @@ extern "C" void bfhe_destroy(bfhe_ctx *c) {
     cudaFree(c->d_bk); cudaFree(c->d_twl); cudaFree(c->d_psiM); cudaFree(c->d_ksk); cudaFree(c->d_gates); cudaFree(c->d_ext);
     cudaFree(c->d_tmp); cudaFree(c->d_ptr_in); cudaFree(c->d_ptr_out); cudaFree(c->e2e_slab);
     cudaFree(c->d_gates_b); cudaFree(c->d_ext_b);
-    cudaFree(c->d_bk2); cudaFree(c->d_bk3); cudaFree(c->d_bk4); cudaFree(c->d_tw2); cudaFree(c->d_F);
+    cudaFree(c->d_bk2); cudaFree(c->d_bk4); cudaFree(c->d_tw2); cudaFree(c->d_F);
     for (int i = 0; i < 2; i++) {
       if (c->ev_br[i]) cudaEventDestroy(c->ev_br[i]);
       if (c->ev_ks[i]) cudaEventDestroy(c->ev_ks[i]);
@@ -356,21 +356,16 @@ int bfhe::ensure_device_keys(bfhe_ctx *c) {
     cudaFree(d_coef);
   }
   cudaFree(c->d_bk2); c->d_bk2 = nullptr; c->v2.d_bk2 = nullptr;
-  cudaFree(c->d_bk3); c->d_bk3 = nullptr; c->v2.d_bk3 = nullptr;
   cudaFree(c->d_bk4); c->d_bk4 = nullptr; c->v2.d_bk4 = nullptr;
   if (c->d_tw2 && v2_supported(c->P, p.method == BFHE_AP)) { // second copy in the physical slot order of kernels_v2.cu
     BFHE_CUDA(cudaMalloc(&c->d_bk2, c->bk_words * 4));
     int rc = launch_bk_permute_v2(c->d_bk, c->d_bk2, c->bk_words / N, c->stream);
     if (rc) return cuda_fail((cudaError_t)rc, "bk_permute_v2");
-    BFHE_CUDA(cudaMalloc(&c->d_bk3, c->bk_words * 4));
-    rc = launch_bk_split_cl2(c->d_bk2, c->d_bk3, c->bk_words / N, c->stream);
-    if (rc) return cuda_fail((cudaError_t)rc, "bk_split_cl2");
     BFHE_CUDA(cudaMalloc(&c->d_bk4, c->bk_words * 4));
     rc = launch_bk_split_cl4(c->d_bk2, c->d_bk4, c->bk_words / N, c->stream);
     if (rc) return cuda_fail((cudaError_t)rc, "bk_split_cl4");
     BFHE_CUDA(cudaStreamSynchronize(c->stream));
     c->v2.d_bk2 = c->d_bk2;
-    c->v2.d_bk3 = c->d_bk3;
     c->v2.d_bk4 = c->d_bk4;
   }
   { // KSK: [i][j(digit value)][k(digit index)][n+1]  ->  [i][k][j][rowlen]

@@ -1180,7 +1180,7 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   // narrower than the number of co-resident 2-CTA clusters: one gate on two SMs (1.49 ms per wave instead of 2.30 ms)
   if (force_g == 0 && have_v2 && v2->d_bk4 && count <= cl4_fast_gates()) // one gate on four SMs (1.19 - 1.26 ms per wave)
     return launch_blind_rotate_cl4(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
-  if (force_g == 0 && have_v2 && v2->d_bk3 && count <= cl2_max_gates())
+  if (force_g == 0 && have_v2 && v2->d_bk4 && count <= cl2_max_gates())
     return launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   const long lat_cost = (long)((count + sms - 1) / sms) * 23;
   const long thr_cost = (long)((count + 4 * sms - 1) / (4 * sms)) * 76;

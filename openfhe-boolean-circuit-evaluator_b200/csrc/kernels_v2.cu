@@ -762,12 +762,13 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   }
   __syncthreads();
   const u32 Z = *(volatile u32 *)&s_zero;
-  // key copy of this kernel: [step][rank][polynomial][HALF] -- each CTA's 64 KB of a step are contiguous (four 16 KB bulk copies;
-  // 32 copies of 2 KB out of the [step][polynomial][N] layout took 2.5 us to land and stalled every step)
+  // key copy of the cluster kernels: [step][quarter of the slots][polynomial][N/4] -- each CTA's 64 KB of a step (two quarters) are
+  // contiguous (four 16 KB bulk copies; 32 copies of 2 KB out of the [step][polynomial][N] layout took 2.5 us to land and stalled
+  // every step).  The 4-CTA kernel reads one quarter of the same copy, so alternating between the two forms keeps the L2 warm.
   auto issue_keys = [&](u32 step) { // the LAST warp (idle while warps 0-1 run the inverse transform)
     if (lane == 0) mbar_expect_tx(s_bar, Cl2Cfg::KEYBYTES);
     __syncwarp();
-    const u32 *src = bk + ((size_t)step * 2 + r) * KEYPOLYS * HALF;
+    const u32 *src = bk + ((size_t)step * 2 + r) * KEYPOLYS * HALF; // = quarters 2r and 2r + 1 of the [step][quarter][polynomial][N/4] copy
     if (lane < 4) bulk_g2s(s_key + (size_t)lane * 4096, src + (size_t)lane * 4096, 16384, s_bar);
   };
   static_assert(Cl2Cfg::KEYBYTES == 4 * 16384, "four bulk copies");
@@ -852,6 +853,7 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     mbar_wait(s_bar, step & 1);
     auto mac = [&](auto RC) {
       constexpr int r = decltype(RC)::value, peer = 1 - r; // compile-time copy of the rank: keeps everything in registers
+      const int kq_off = ((2 * tid) >> 8) * KEYPOLYS * (HALF / 2), kq_in = (2 * tid) & (HALF / 2 - 1); // tile = [quarter][polynomial][N/4]
       const u32 m = s_idx[step];
       u32 fp[2], fn[2];
 #pragma unroll
@@ -867,8 +869,8 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
         const uint2 d = *reinterpret_cast<const uint2 *>(rows + (size_t)l * N + o);
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
-          const uint2 kp = *reinterpret_cast<const uint2 *>(s_key + (size_t)((0 * ROWS + 2 * l + r) * 2 + cc) * HALF + 2 * tid);
-          const uint2 kn = *reinterpret_cast<const uint2 *>(s_key + (size_t)((1 * ROWS + 2 * l + r) * 2 + cc) * HALF + 2 * tid);
+          const uint2 kp = *reinterpret_cast<const uint2 *>(s_key + kq_off + (size_t)((0 * ROWS + 2 * l + r) * 2 + cc) * (HALF / 2) + kq_in);
+          const uint2 kn = *reinterpret_cast<const uint2 *>(s_key + kq_off + (size_t)((1 * ROWS + 2 * l + r) * 2 + cc) * (HALF / 2) + kq_in);
           sp[cc][0] += (u64)d.x * kp.x; sp[cc][1] += (u64)d.y * kp.y;
           sn[cc][0] += (u64)d.x * kn.x; sn[cc][1] += (u64)d.y * kn.y;
         }
@@ -879,8 +881,8 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
         const uint2 d = *reinterpret_cast<const uint2 *>(stage + (size_t)l * HALF + 2 * tid);
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
-          const uint2 kp = *reinterpret_cast<const uint2 *>(s_key + (size_t)((0 * ROWS + 2 * l + peer) * 2 + cc) * HALF + 2 * tid);
-          const uint2 kn = *reinterpret_cast<const uint2 *>(s_key + (size_t)((1 * ROWS + 2 * l + peer) * 2 + cc) * HALF + 2 * tid);
+          const uint2 kp = *reinterpret_cast<const uint2 *>(s_key + kq_off + (size_t)((0 * ROWS + 2 * l + peer) * 2 + cc) * (HALF / 2) + kq_in);
+          const uint2 kn = *reinterpret_cast<const uint2 *>(s_key + kq_off + (size_t)((1 * ROWS + 2 * l + peer) * 2 + cc) * (HALF / 2) + kq_in);
           sp[cc][0] += (u64)d.x * kp.x; sp[cc][1] += (u64)d.y * kp.y;
           sn[cc][0] += (u64)d.x * kn.x; sn[cc][1] += (u64)d.y * kn.y;
         }
@@ -1135,23 +1137,13 @@ blind_rotate_cl4_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   cluster_sync_all(); // a CTA must not exit while its peers may still push into its shared memory
 }
 
-// key copy of the 4-CTA kernel: [step][polynomial][N] -> [step][rank][polynomial][N/4]
+// key copy of the cluster kernels: [step][polynomial][N] -> [step][quarter][polynomial][N/4]
 __global__ void bk_split_cl4_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t nsteps) {
   constexpr int KP = Cl4Cfg::KEYPOLYS, QUARTER = Cl4Cfg::QUARTER;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsteps * KP * N; i += (size_t)gridDim.x * blockDim.x) {
     const size_t step = i / ((size_t)KP * N), rem = i % ((size_t)KP * N);
     const int pl = (int)(rem / N), o = (int)(rem % N), rk = o / QUARTER;
     dst[((step * 4 + rk) * KP + pl) * QUARTER + (o % QUARTER)] = src[i];
-  }
-}
-
-// key copy of the cluster kernel: [step][polynomial][N] -> [step][rank][polynomial][N/2]
-__global__ void bk_split_cl2_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t nsteps) {
-  constexpr int KP = Cl2Cfg::KEYPOLYS, HALF = Cl2Cfg::HALF;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsteps * KP * N; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t step = i / ((size_t)KP * N), rem = i % ((size_t)KP * N);
-    const int pl = (int)(rem / N), o = (int)(rem % N), rk = o / HALF;
-    dst[((step * 2 + rk) * KP + pl) * HALF + (o % HALF)] = src[i];
   }
 }
 
@@ -1245,13 +1237,8 @@ int launch_blind_rotate_cl2(const DevConst &P, const DevGate *d_gates, int count
     attr_done = true;
   }
   if (info) { info->gates_per_cta = 1; info->ctas = 2 * count; info->smem_bytes = v2::Cl2Cfg::smem_bytes; }
-  v2::blind_rotate_cl2_kernel<<<2 * count, v2::Cl2Cfg::THREADS, v2::Cl2Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk3, vb.d_tw2,
+  v2::blind_rotate_cl2_kernel<<<2 * count, v2::Cl2Cfg::THREADS, v2::Cl2Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk4, vb.d_tw2,
                                                                                                          vb.d_F, d_ext, d_acc_dbg);
-  return (int)cudaGetLastError();
-}
-int launch_bk_split_cl2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
-  if (npoly == 0) return 0;
-  v2::bk_split_cl2_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly / v2::Cl2Cfg::KEYPOLYS);
   return (int)cudaGetLastError();
 }
 int launch_bk_permute_v2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
