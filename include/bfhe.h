@@ -112,6 +112,8 @@ int bfhe_dbg_ntt_roundtrip(bfhe_ctx *, const uint32_t *poly_host, size_t npoly, 
 int bfhe_dbg_blind_rotate(bfhe_ctx *, uint32_t *dev_slab, const bfhe_gate *gates, size_t count, uint32_t *acc_host);
 /* test hook: force the number of gates one CTA carries (1, 2 or 4; 0 = choose from the batch size) */
 int bfhe_dbg_set_gates_per_cta(bfhe_ctx *, int gates_per_cta);
+/* how many gates the 2-CTA / 4-CTA cluster forms keep co-resident on this device (cudaOccupancyMaxActiveClusters; differs between GPUs) */
+int bfhe_dbg_cluster_limits(bfhe_ctx *, int *cl2_gates, int *cl4_gates);
 
 /* ---- circuit evaluator: mirrors class Circuit (src/circuit.h:56-72), level-synchronous ---- */
 typedef struct bfhe_circuit bfhe_circuit;

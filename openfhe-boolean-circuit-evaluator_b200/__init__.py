@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "bfhe_load_keys", "bfhe_encrypt", "bfhe_decrypt", "bfhe_slab_alloc", "bfhe_slab_free", "bfhe_slab_upload",
     "bfhe_slab_download", "bfhe_eval_not_batch", "bfhe_eval_bingate_batch", "bfhe_bootstrap_batch",
     "bfhe_eval_bingate_host", "bfhe_profile_enable", "bfhe_profile_read", "bfhe_microbench_int",
-    "bfhe_dbg_ntt_roundtrip", "bfhe_dbg_blind_rotate", "bfhe_dbg_set_gates_per_cta",
+    "bfhe_dbg_ntt_roundtrip", "bfhe_dbg_blind_rotate", "bfhe_dbg_set_gates_per_cta", "bfhe_dbg_cluster_limits",
     "bfhe_circuit_create", "bfhe_circuit_destroy", "bfhe_circuit_read_file", "bfhe_circuit_read_bristol",
     "bfhe_circuit_set_flags", "bfhe_circuit_info", "bfhe_circuit_set_sharding", "bfhe_get_nccl_unique_id",
     "bfhe_circuit_set_wave_capacity",
@@ -97,6 +97,7 @@ def lib():
     L.bfhe_dbg_ntt_roundtrip.argtypes = [vp, vp, sz, vp, vp, vp]
     L.bfhe_dbg_blind_rotate.argtypes = [vp, vp, vp, sz, vp]
     L.bfhe_dbg_set_gates_per_cta.argtypes = [vp, C.c_int]
+    L.bfhe_dbg_cluster_limits.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.bfhe_circuit_create.restype = vp
     L.bfhe_circuit_create.argtypes = [vp]
     L.bfhe_circuit_destroy.restype = None
@@ -309,6 +310,11 @@ class Context:
 
     def dbg_set_gates_per_cta(self, g):
         self._ck(self.L.bfhe_dbg_set_gates_per_cta(self.h, g))
+
+    def dbg_cluster_limits(self):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.L.bfhe_dbg_cluster_limits(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
 
 def nccl_unique_id():

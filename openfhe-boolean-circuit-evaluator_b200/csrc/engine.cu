@@ -840,6 +840,13 @@ extern "C" int bfhe_dbg_blind_rotate(bfhe_ctx *c, uint32_t *slab, const bfhe_gat
   return eval_batch_locked(c, slab, gates, count, acc_host);
 }
 
+extern "C" int bfhe_dbg_cluster_limits(bfhe_ctx *c, int *cl2_gates, int *cl4_gates) {
+  if (!c || c->device < 0) return BFHE_ERR_ARG;
+  BFHE_CUDA(cudaSetDevice(c->device));
+  if (cl2_gates) *cl2_gates = cl2_max_gates();
+  if (cl4_gates) *cl4_gates = cl4_max_gates();
+  return BFHE_OK;
+}
 extern "C" int bfhe_dbg_set_gates_per_cta(bfhe_ctx *c, int g) {
   if (!c) return BFHE_ERR_ARG;
   c->force_g = g;

@@ -1180,7 +1180,10 @@ template <typename K> static int max_active_clusters(K kern, int cluster, int th
   cfg.numAttrs = 1;
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-  return n;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return n < sms / cluster ? n : sms / cluster; // one CTA per SM: two co-resident CTAs of these kernels would just share the pipe
 }
 int cl4_max_gates() {
   static int cached = -1;
@@ -1212,20 +1215,8 @@ int launch_blind_rotate_cl4(const DevConst &P, const DevGate *d_gates, int count
 // how many gates the cluster form runs at once (2-CTA clusters must sit inside one GPC, so this can be less than SMs / 2)
 int cl2_max_gates() {
   static int cached = -1;
-  if (cached >= 0) return cached;
-  if (v2_set_attrs()) return cached = 0;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * 148, 1, 1);
-  cfg.blockDim = dim3(v2::Cl2Cfg::THREADS, 1, 1);
-  cfg.dynamicSmemBytes = v2::Cl2Cfg::smem_bytes;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, v2::blind_rotate_cl2_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-  return cached = n;
+  if (cached < 0) cached = max_active_clusters(v2::blind_rotate_cl2_kernel, 2, v2::Cl2Cfg::THREADS, v2::Cl2Cfg::smem_bytes);
+  return cached;
 }
 int launch_blind_rotate_cl2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
                             LaunchInfo *info) {

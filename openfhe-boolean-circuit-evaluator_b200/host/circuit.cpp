@@ -150,8 +150,12 @@ static int build_plan(bfhe_circuit *c) {
   if (c->wave_cap_req >= 0 || !c->ctx || c->ctx->device < 0) return build_plan_cap(c, c->wave_cap_req > 0 ? (uint32_t)c->wave_cap_req : 0);
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->ctx->device) != cudaSuccess || sms <= 0) return build_plan_cap(c, 0);
+  // The schedule must be the same on every rank, so the cluster-form capacities come from the SM count alone, not from this
+  // device's cudaOccupancyMaxActiveClusters (which differs between GPUs of one box: 74 and 63 two-CTA clusters were both seen on
+  // 148-SM B200s): 5/12 of the SMs for one gate on two SMs, 2/9 for one gate on four.  A wave that a particular GPU cannot keep
+  // co-resident in the planned form simply runs in the next form there (launch_blind_rotate checks the real limit).
   const bool clusters = c->ctx->v2.d_tw2 && c->ctx->p.method == BFHE_GINX;
-  const int cl2 = clusters ? cl2_max_gates() : 0, cl4 = clusters ? cl4_fast_gates() : 0;
+  const int cl2 = clusters ? sms * 5 / 12 : 0, cl4 = clusters ? sms * 2 / 9 : 0;
   uint32_t cands[4] = {0u, (uint32_t)sms * (uint32_t)c->world, (uint32_t)cl2 * (uint32_t)c->world, (uint32_t)cl4 * (uint32_t)c->world};
   uint32_t best = 0;
   double best_t = 0;
