@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, nvec, q):
+def _worker(rank, world, port, name, nvec, q, cap=0):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import bfhe_loader
@@ -39,6 +39,7 @@ def _worker(rank, world, port, name, nvec, q):
     o.import_keys(blob.numpy())
     circ = load_circuit(B, ctx, name)
     circ.set_sharding(rank, world)
+    circ.set_wave_capacity(cap)  # 0 = the reference's ASAP waves; > 0 = packed waves (must be identical on every rank)
 
     def gather(blk, r, rpr):
         mine = torch.from_numpy(np.ascontiguousarray(blk[r * rpr:(r + 1) * rpr]).astype(np.int32))
@@ -62,12 +63,12 @@ def _worker(rank, world, port, name, nvec, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,nvec", [("adder_2bit", 3), ("parity", 2)])
-def test_world2_gloo_sharded_levels(name, nvec):
+@pytest.mark.parametrize("name,nvec,cap", [("adder_2bit", 3, 0), ("parity", 2, 0), ("parity", 2, 4)])
+def test_world2_gloo_sharded_levels(name, nvec, cap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 200) + (0 if name == "adder_2bit" else 1)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, nvec, q)) for r in range(2)]
+    port = 29600 + (os.getpid() % 200) + (0 if name == "adder_2bit" else 1) + 2 * (cap > 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, nvec, q, cap)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
