@@ -1,6 +1,9 @@
-// kernels_v2.cu -- second-generation throughput kernel for the GINX blind rotation (STD128_OPT shape: N = 1024, dG = 4,
-// Bg = 2^7).  Same arithmetic as blind_rotate_kernel in kernels.cu (the reference reaches it
-// through BinFHEContext::EvalBinGate, src/gate.cpp:133,172,200-202 in /root/reference), different mapping to the SM:
+// kernels_v2.cu -- the GINX blind rotation on 16-value / 8-value register tiles (STD128_OPT shape: N = 1024, dG = 4, Bg = 2^7):
+//   blind_rotate_v2_kernel   four gates per CTA, 16 warps (throughput form, measured equal to kernels.cu's; selectable, not default)
+//   blind_rotate_cl2_kernel  ONE gate on a 2-CTA thread-block cluster (waves of 34..74 gates)          } data exchanged over DSMEM
+//   blind_rotate_cl4_kernel  ONE gate on a 4-CTA thread-block cluster (waves of up to 33 gates)        } with st.async + mbarrier
+// Same arithmetic as blind_rotate_kernel in kernels.cu (the reference reaches it through
+// BinFHEContext::EvalBinGate, src/gate.cpp:133,172,200-202 in /root/reference), different mappings to the SM.  The throughput form:
 //
 //  * 16 warps per CTA instead of 8 (<= 128 registers per thread): every transform works on 16-value register tiles
 //    (three passes 4 + 3 + 3 stages with two in-place shared-memory transposes) instead of 32-value tiles.  Four warps
