@@ -320,30 +320,33 @@ def peak_hbm():
 
 
 def aux_circuits(B, ctx, rank, world):
-    """AES-128 whole-circuit wall time (BASELINE config 5), levels sharded over the ranks with ncclAllGather."""
+    """AES-128 and SHA-256 whole-circuit wall time (BASELINE config 5), waves sharded over the ranks with ncclAllGather.
+    AES: second of two evaluations (the first builds the CUDA graph); SHA-256 (13 s of depth-bound work): one evaluation."""
     import torch
     import torch.distributed as dist
-    path = os.path.join(ROOT, "tests", "golden", "circuits", "AES-non-expanded.npz")
-    vec = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["AES-non-expanded"]["vectors"][1]
-    c = B.Circuit(ctx)
-    c.load_npz(path)
-    if world > 1:
-        uid = torch.from_numpy(B.nccl_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
-        dist.broadcast(uid, 0)
-        c.set_sharding(rank, world, uid.cpu().numpy())
+    vectors = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))
     res = {}
-    for rep in range(2):
-        c.Reset()
-        c.setEncrypted(True)
-        c.SetInput(vec["inputs"], seed=7)
+    for name, key, reps in (("AES-non-expanded", "aes128", 2), ("sha256", "sha256", 1)):
+        vec = vectors[name]["vectors"][1]
+        c = B.Circuit(ctx)
+        c.load_npz(os.path.join(ROOT, "tests", "golden", "circuits", name + ".npz"))
         if world > 1:
-            dist.barrier()
-        t = time.perf_counter()
-        out = c.Clock()[0]
-        wall = time.perf_counter() - t
-        res = {"aes128_wall_ms": 1e3 * wall, "aes128_device_ms": c.stats()["device_ms"], "aes128_kat_ok": out == vec["golden"],
-               "aes128_bootstraps": c.info()["bootstraps"], "aes128_levels": c.info()["levels"]}
-    c.close()
+            uid = torch.from_numpy(B.nccl_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
+            dist.broadcast(uid, 0)
+            c.set_sharding(rank, world, uid.cpu().numpy())
+        for rep in range(reps):
+            c.Reset()
+            c.setEncrypted(True)
+            c.SetInput(vec["inputs"], seed=7)
+            if world > 1:
+                dist.barrier()
+            t = time.perf_counter()
+            out = c.Clock()[0]
+            wall = time.perf_counter() - t
+            res.update({key + "_wall_ms": 1e3 * wall, key + "_device_ms": c.stats()["device_ms"], key + "_kat_ok": out == vec["golden"],
+                        key + "_bootstraps": c.info()["bootstraps"], key + "_levels": c.info()["levels"],
+                        key + "_waves": c.plan_misc()["n_levels"] - 1})
+        c.close()
     return res
 
 
