@@ -1188,10 +1188,26 @@ template <typename K> static int max_active_clusters(K kern, int cluster, int th
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return n < sms / cluster ? n : sms / cluster; // one CTA per SM: two co-resident CTAs of these kernels would just share the pipe
 }
+static int current_device_slot();
+static int v2_attrs_once() { // function attributes are per device and must not be set under stream capture: once, at first use
+  static bool done[64];
+  const int d = current_device_slot();
+  if (done[d]) return 0;
+  const int rc = v2_set_attrs();
+  if (rc == 0) done[d] = true;
+  return rc;
+}
+static int current_device_slot() { // the limits are per device (one process may hold contexts on several)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < 64 ? dev : 0;
+}
 int cl4_max_gates() {
-  static int cached = -1;
-  if (cached < 0) cached = max_active_clusters(v2::blind_rotate_cl4_kernel, 4, v2::Cl4Cfg::THREADS, v2::Cl4Cfg::smem_bytes);
-  return cached;
+  static int cached[64];
+  static bool have[64];
+  const int d = current_device_slot();
+  if (!have[d]) { cached[d] = max_active_clusters(v2::blind_rotate_cl4_kernel, 4, v2::Cl4Cfg::THREADS, v2::Cl4Cfg::smem_bytes); have[d] = true; }
+  return cached[d];
 }
 // The 4-CTA form slows down when (almost) every SM carries a cluster: measured on B200 1.19 ms up to 30 gates, 1.26 ms for 31-33,
 // 1.59 ms for 34-37 (37 = co-resident maximum) -- above ~7/8 of the maximum the 2-CTA form (1.49 ms up to 74 gates) is the better one.
@@ -1204,12 +1220,7 @@ int launch_bk_split_cl4(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream
 int launch_blind_rotate_cl4(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
                             LaunchInfo *info) {
   if (count <= 0) return 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int rc = v2_set_attrs();
-    if (rc) return rc;
-    attr_done = true;
-  }
+  if (int rc = v2_attrs_once()) return rc;
   if (info) { info->gates_per_cta = 1; info->ctas = 4 * count; info->smem_bytes = v2::Cl4Cfg::smem_bytes; }
   v2::blind_rotate_cl4_kernel<<<4 * count, v2::Cl4Cfg::THREADS, v2::Cl4Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk4, vb.d_tw2,
                                                                                                          vb.d_F, d_ext, d_acc_dbg);
@@ -1217,19 +1228,16 @@ int launch_blind_rotate_cl4(const DevConst &P, const DevGate *d_gates, int count
 }
 // how many gates the cluster form runs at once (2-CTA clusters must sit inside one GPC, so this can be less than SMs / 2)
 int cl2_max_gates() {
-  static int cached = -1;
-  if (cached < 0) cached = max_active_clusters(v2::blind_rotate_cl2_kernel, 2, v2::Cl2Cfg::THREADS, v2::Cl2Cfg::smem_bytes);
-  return cached;
+  static int cached[64];
+  static bool have[64];
+  const int d = current_device_slot();
+  if (!have[d]) { cached[d] = max_active_clusters(v2::blind_rotate_cl2_kernel, 2, v2::Cl2Cfg::THREADS, v2::Cl2Cfg::smem_bytes); have[d] = true; }
+  return cached[d];
 }
 int launch_blind_rotate_cl2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
                             LaunchInfo *info) {
   if (count <= 0) return 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int rc = v2_set_attrs();
-    if (rc) return rc;
-    attr_done = true;
-  }
+  if (int rc = v2_attrs_once()) return rc;
   if (info) { info->gates_per_cta = 1; info->ctas = 2 * count; info->smem_bytes = v2::Cl2Cfg::smem_bytes; }
   v2::blind_rotate_cl2_kernel<<<2 * count, v2::Cl2Cfg::THREADS, v2::Cl2Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk4, vb.d_tw2,
                                                                                                          vb.d_F, d_ext, d_acc_dbg);
@@ -1243,12 +1251,7 @@ int launch_bk_permute_v2(const u32 *d_src, u32 *d_dst, size_t npoly, void *strea
 int launch_blind_rotate_v2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
                            LaunchInfo *info) {
   if (count <= 0) return 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int rc = v2_set_attrs();
-    if (rc) return rc;
-    attr_done = true;
-  }
+  if (int rc = v2_attrs_once()) return rc;
   const int ctas = (count + v2::G - 1) / v2::G;
   if (info) { info->gates_per_cta = v2::G; info->ctas = ctas; info->smem_bytes = v2::Cfg::smem_bytes; }
   v2::blind_rotate_v2_kernel<<<ctas, v2::THREADS, v2::Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk2, vb.d_tw2, vb.d_F, d_ext,

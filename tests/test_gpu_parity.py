@@ -181,3 +181,13 @@ def test_empty_and_multi_chunk_batches(bfhe, orc):
     o.eval_gates(gates[sel], ref)
     w = ctx.p.ct_words
     assert np.array_equal(out[sel][:, :w], ref[n_in + sel][:, :w])
+
+
+def test_cluster_limits_are_sane(bfhe):
+    """The cluster forms run one CTA per SM: at most SMs/2 two-CTA and SMs/4 four-CTA clusters co-resident (the per-device numbers the
+    launch cost model uses; the circuit planner deliberately does not)."""
+    import torch
+    ctx = shared_keys(bfhe, bfhe.STD128_OPT, bfhe.GINX, 0)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    cl2, cl4 = ctx.dbg_cluster_limits()
+    assert 0 < cl2 <= sms // 2 and 0 < cl4 <= sms // 4
