@@ -151,8 +151,8 @@ def test_wave_packing_is_a_valid_schedule(bfhe, hctx, name, cap):
     assert c.plan_misc()["n_levels"] - 1 == asap_levels
 
 
-@pytest.mark.parametrize("name", ["adder_2bit", "parity"])
-def test_wave_packing_keeps_ciphertexts(bfhe, orc, hctx, name):
+@pytest.mark.parametrize("name,cap", [("adder_2bit", 2), ("parity", 2), ("comparator_32bit_signed_lteq", 7)])
+def test_wave_packing_keeps_ciphertexts(bfhe, orc, hctx, name, cap):
     """Same keys, same fresh encryptions: the packed schedule produces bit-identical output ciphertexts (oracle as executor)."""
     from helpers import oracle_run_plan
     o = orc.Oracle(orc.TOY, orc.GINX)
@@ -161,7 +161,7 @@ def test_wave_packing_keeps_ciphertexts(bfhe, orc, hctx, name):
     c = load_circuit(bfhe, bfhe.Context(bfhe.TOY, bfhe.GINX, device=-1), name)
     outs0, slab0 = oracle_run_plan(c, o, v["inputs"], seed=3)
     rows0 = [int(r) & 0x7fffffff for r in c.plan_misc()["out_rows"]]
-    c.set_wave_capacity(2)
+    c.set_wave_capacity(cap)
     outs1, slab1 = oracle_run_plan(c, o, v["inputs"], seed=3)
     rows1 = [int(r) & 0x7fffffff for r in c.plan_misc()["out_rows"]]
     assert outs0 == outs1 == v["golden"]
