@@ -56,8 +56,8 @@ template <bool SOL = false> __device__ __forceinline__ u32 mul_shoup(u32 x, u32 
 }
 // per-pass stage masks (bit i = stage i of the pass uses the ALU form); tuned with tools/perf_g.py / phase_timing.py
 #ifndef BFHE_SOL_THR_WIDE
-#define BFHE_SOL_THR_WIDE 0x17
-#define BFHE_SOL_THR_NARROW 0x0b
+#define BFHE_SOL_THR_WIDE 0x00 // re-measured after the first-stage product table: 0x00/0x00 80.2k, 0x07/0x03 80.3k, 0x17/0x0b 79.7k,
+#define BFHE_SOL_THR_NARROW 0x00 // 0x1f/0x1f 77.1k gates/s -- within noise of each other except all-on; kept off
 #define BFHE_SOL_LAT_WIDE 0x05
 #define BFHE_SOL_LAT_NARROW 0x0a
 #define BFHE_SOL_LAT_INV 0x00
