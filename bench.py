@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--gates", type=int, default=0,
                     help="gates per rank per step (config 3 mix); 0 = 42 full waves of 4-gate CTAs (24 864 on a 148-SM B200)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-aux", action="store_true", help="skip the AES-128 circuit wall-time figure")
+    ap.add_argument("--no-aux", action="store_true", help="skip the AES-128 / SHA-256 circuit wall-time figures")
     ap.add_argument("--cpu-sample", type=int, default=0, help="gates in the CPU baseline sample (0 = 16 per core; reference arm: 8 per core per step)")
     return ap.parse_args()
 

@@ -134,6 +134,9 @@ template <int E> __device__ __forceinline__ void load_lane_tw(const u32 *tab, u3
 #ifndef BFHE_PAIRED_DIGITS
 #define BFHE_PAIRED_DIGITS 1
 #endif
+#ifndef BFHE_PAIRED_MAXG
+#define BFHE_PAIRED_MAXG 2
+#endif
 __device__ __forceinline__ u32 comp4(const uint4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 // PRE: the products of the FIRST stage arrive precomputed in pre[0 .. E/2) (digit transforms: twiddle * small digit comes
 // from a 128-entry table, see blind_rotate_kernel), x[E/2 ..) is not read.
@@ -460,7 +463,7 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
       }
       // two digits per pass (STD128_OPT shape): +8 % at two gates per CTA (71.3k -> 77.0k gates/s), nothing at four (79.3k vs 79.7k),
       // where the phase is already within ~20 % of its pipe bound (tools/phase_timing.py) -- used for G <= 2 only
-      constexpr bool PAIRED = Cfg::LUT && !LEAN && (DG % 2 == 0) && G <= 2 && BFHE_PAIRED_DIGITS;
+      constexpr bool PAIRED = Cfg::LUT && !LEAN && (DG % 2 == 0) && G <= BFHE_PAIRED_MAXG && BFHE_PAIRED_DIGITS;
       if constexpr (PAIRED) {
 #pragma unroll
         for (int l = 0; l < DG; l += 2) {
