@@ -62,7 +62,12 @@ const char *bfhe_last_error(void);
 int bfhe_set_stream(bfhe_ctx *, void *cuda_stream, int use_own);
 int bfhe_sync(bfhe_ctx *);
 
-/* ---- keys: KeyGen() / BTKeyGen(sk)  (src/circuit.cpp:90-91) ---- */
+/* ---- keys: KeyGen() / BTKeyGen(sk)  (src/circuit.cpp:90-91) ----
+ * Randomness contract (keygen, btkeygen, encrypt, circuit_set_input): every secret, mask and noise term is drawn from a ChaCha20
+ * stream.  seed == 0 keys the stream with 256 bits of OS entropy (getrandom): the secure default, equivalent to OpenFHE's self-seeding
+ * PRNG that the reference relies on.  seed != 0 derives the stream from the 64-bit seed alone: reproducible keys / ciphertexts for
+ * tests, oracle parity and benchmarks, and therefore NOT confidential.  For sharded (multi-rank) evaluation generate the keys on one
+ * rank with seed 0 and distribute the blob (bfhe_export_keys -> broadcast -> bfhe_import_keys); do not share a constant seed. */
 int bfhe_keygen(bfhe_ctx *, uint64_t seed);   /* LWE secret key (host) */
 int bfhe_btkeygen(bfhe_ctx *, uint64_t seed); /* bootstrapping + key-switching keys (host), uploaded if a device is attached */
 /* flat key blob ("same serialized keys" contract, SURVEY 5 checkpoint/resume): layout documented in DESIGN.md:
@@ -124,9 +129,17 @@ void bfhe_circuit_destroy(bfhe_circuit *);
 int bfhe_circuit_read_file(bfhe_circuit *, const char *path);             /* Circuit::ReadFile (.out assembler format) */
 int bfhe_circuit_read_bristol(bfhe_circuit *, const char *path, int new_format); /* analyze+assemble without the text round trip */
 /* netlist from arrays / back to arrays / emitted as the reference's ".out" text.  kind[] uses GateEnum order
- * {INPUT, OUTPUT, NOT, AND, OR, XOR} (src/gate.h:51); INPUT: in0 = bus, in1 = bit, out = wire; OUTPUT: in0 = wire, out = bit */
+ * {INPUT, OUTPUT, NOT, AND, OR, XOR, DFF, LUT3, LUT4} (src/gate.h:51), then the native single-bootstrap gate types of EvalBinGate and
+ * the composite XNOR: {NAND, NOR, XNOR, XOR_FAST, XNOR_FAST}.  INPUT: in0 = bus, in1 = bit, out = wire; OUTPUT: in0 = wire, out = bit;
+ * DFF: in0 = D, out = Q (state 0 after Reset; Clock() may be called repeatedly, each call latches D -- the reason the reference's
+ * method is called Clock(), README.md:55); LUT3 / LUT4 (stubs in the reference, src/gate.cpp:220-225): in0..in3 and a truth table whose
+ * bit (in0 | in1 << 1 | in2 << 2 | in3 << 3) is the output, lowered at load to <= 5 / <= 13 two-input gates (_ex entry point).
+ * ".out" grammar of the additions: "R3 = NAND(R1, R2)", "R5 = DFF(R4)", "R9 = LUT3(R1, R2, R3, 0xE8)", "R9 = LUT4(R1, R2, R3, R4, 0x6996)". */
 int bfhe_circuit_load_netlist(bfhe_circuit *, const uint8_t *kind, const uint32_t *in0, const uint32_t *in1, const uint32_t *out,
                               size_t count, uint32_t n_wires, const uint32_t *in_bits, uint32_t n_in_buses, uint32_t out_bits);
+int bfhe_circuit_load_netlist_ex(bfhe_circuit *, const uint8_t *kind, const uint32_t *in0, const uint32_t *in1, const uint32_t *in2,
+                                 const uint32_t *in3, const uint32_t *table, const uint32_t *out, size_t count, uint32_t n_wires,
+                                 const uint32_t *in_bits, uint32_t n_in_buses, uint32_t out_bits);
 int bfhe_circuit_get_netlist(const bfhe_circuit *, uint8_t *kind, uint32_t *in0, uint32_t *in1, uint32_t *out, size_t cap,
                              uint32_t *count, uint32_t *n_wires);
 int bfhe_circuit_write_out(const bfhe_circuit *, const char *path);
@@ -140,11 +153,15 @@ int bfhe_get_nccl_unique_id(void *out128);
  * waves of at most n bootstraps by longest remaining path; -1 (default) = one gate per SM and rank when a device is attached,
  * ASAP otherwise.  Ciphertexts do not depend on the schedule.  bfhe_circuit_info always reports the ASAP statistics. */
 int bfhe_circuit_set_wave_capacity(bfhe_circuit *, int max_bootstraps_per_wave);
+/* multi-GPU: levels with fewer than min_bootstraps bootstraps are computed redundantly by every rank and skip the exchange
+ * (SURVEY 8(e)); 0 = shard every level; -1 (default) = per level by the measured cost model (device attached), else shard all */
+int bfhe_circuit_set_shard_threshold(bfhe_circuit *, int min_bootstraps);
 int bfhe_circuit_reset(bfhe_circuit *);                                     /* Circuit::Reset */
 int bfhe_circuit_set_input(bfhe_circuit *, const uint8_t *bits, size_t nbits, uint64_t seed); /* Circuit::SetInput (all input buses concatenated) */
 int bfhe_circuit_clock(bfhe_circuit *, uint8_t *out_bits, size_t cap, uint8_t *plain_out_bits); /* Circuit::Clock */
 int bfhe_circuit_stats(const bfhe_circuit *, double *device_ms, double *host_ms, uint64_t *verify_mismatches);
-/* per-level plan, for tests of the sharding logic: gates of level L assigned to `rank` of `world` */
+/* per-level plan, for tests of the sharding logic: gates of level L assigned to `rank` of `world`; *rows_per_rank == 0 with
+ * world > 1 means the level is not sharded (every rank evaluates all of it, no exchange follows) */
 int bfhe_circuit_level_plan(const bfhe_circuit *, uint32_t level, int rank, int world, bfhe_gate *out, size_t cap,
                             uint32_t *count, uint32_t *first_row, uint32_t *rows_per_rank);
 /* plan internals for tests: total slab rows, first fresh-encryption row, level count incl. the input-bootstrap
@@ -155,6 +172,13 @@ int bfhe_circuit_use_graph(bfhe_circuit *, int on); /* one CUDA graph per circui
 int bfhe_circuit_download_slab(bfhe_circuit *, uint32_t *host, size_t rows_cap); /* every wire ciphertext, for parity tests */
 int bfhe_circuit_dump_gate_count(const bfhe_circuit *, uint32_t *in, uint32_t *out, uint32_t *and_, uint32_t *or_,
                                  uint32_t *xor_, uint32_t *not_);
+int bfhe_circuit_dump_gate_count_ex(const bfhe_circuit *, uint32_t *counts8 /* DFF, LUT3, LUT4, NAND, NOR, XNOR, XOR_FAST, XNOR_FAST */);
+/* Circuit::dumpNetList (what = 0: wire name -> names of the gates reading it, in the reference's map order) / Circuit::dumpGates
+ * (what = 1: input gate names, then all gate names) as text (src/circuit.cpp:844-865); *needed = length without the final 0 */
+int bfhe_circuit_dump_text(const bfhe_circuit *, int what, char *buf, size_t cap, size_t *needed);
+/* clocked circuits, for tests of the plan: per flip-flop {row D is read from | bit 31 = through EvalNOT, state row (Q), latch row,
+ * row of the fresh Encrypt(0) that the first clock after Reset bootstraps into the latch row} */
+int bfhe_circuit_dff_plan(const bfhe_circuit *, uint32_t *n_dff, uint32_t *quads, size_t cap_dffs);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,9 @@ OR, AND, NOR, NAND, XOR_FAST, XNOR_FAST, XOR, XNOR, BOOTSTRAP = range(9)
 NEG0, NEG1 = 0x100, 0x200
 ERR_ARG, ERR_STATE, ERR_CUDA, ERR_FORMAT, ERR_ALIAS, ERR_NCCL, ERR_IO = -1, -2, -3, -4, -5, -6, -7
 
+# netlist gate kinds: GateEnum of the reference (src/gate.h:51), then EvalBinGate's other native gate types
+(K_INPUT, K_OUTPUT, K_NOT, K_AND, K_OR, K_XOR, K_DFF, K_LUT3, K_LUT4, K_NAND, K_NOR, K_XNOR, K_XOR_FAST, K_XNOR_FAST) = range(14)
+
 GATE_DTYPE = np.dtype([("op", "<u4"), ("in0", "<u4"), ("in1", "<u4"), ("out", "<u4")])
 
 
@@ -51,6 +54,8 @@ ABI_SYMBOLS = [
     "bfhe_circuit_reset", "bfhe_circuit_set_input", "bfhe_circuit_clock", "bfhe_circuit_stats",
     "bfhe_circuit_level_plan", "bfhe_circuit_plan_misc", "bfhe_circuit_use_graph", "bfhe_circuit_download_slab",
     "bfhe_circuit_dump_gate_count", "bfhe_circuit_load_netlist", "bfhe_circuit_get_netlist", "bfhe_circuit_write_out",
+    "bfhe_circuit_load_netlist_ex", "bfhe_circuit_set_shard_threshold", "bfhe_circuit_dump_gate_count_ex",
+    "bfhe_circuit_dump_text", "bfhe_circuit_dff_plan",
 ]
 
 _lib = None
@@ -121,6 +126,11 @@ def lib():
     L.bfhe_circuit_load_netlist.argtypes = [vp, vp, vp, vp, vp, sz, C.c_uint32, vp, C.c_uint32, C.c_uint32]
     L.bfhe_circuit_get_netlist.argtypes = [vp, vp, vp, vp, vp, sz, u32p, u32p]
     L.bfhe_circuit_write_out.argtypes = [vp, C.c_char_p]
+    L.bfhe_circuit_load_netlist_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, sz, C.c_uint32, vp, C.c_uint32, C.c_uint32]
+    L.bfhe_circuit_set_shard_threshold.argtypes = [vp, C.c_int]
+    L.bfhe_circuit_dump_gate_count_ex.argtypes = [vp, u32p]
+    L.bfhe_circuit_dump_text.argtypes = [vp, C.c_int, C.c_char_p, sz, C.POINTER(sz)]
+    L.bfhe_circuit_dff_plan.argtypes = [vp, u32p, vp, sz]
     _lib = L
     return L
 
@@ -363,6 +373,13 @@ class Circuit:
         self._ck(self.L.bfhe_circuit_load_netlist(self.h, _ptr(kind), _ptr(in0), _ptr(in1), _ptr(out), kind.size, int(n_wires),
                                                   _ptr(ib), ib.size, int(out_bits)))
 
+    def load_netlist_ex(self, kind, in0, in1, in2, in3, table, out, n_wires, in_bits, out_bits):
+        kind = np.ascontiguousarray(kind, dtype=np.uint8)
+        in0, in1, in2, in3, table, out = (np.ascontiguousarray(a, dtype=np.uint32) for a in (in0, in1, in2, in3, table, out))
+        ib = np.ascontiguousarray(in_bits, dtype=np.uint32)
+        self._ck(self.L.bfhe_circuit_load_netlist_ex(self.h, _ptr(kind), _ptr(in0), _ptr(in1), _ptr(in2), _ptr(in3), _ptr(table), _ptr(out),
+                                                     kind.size, int(n_wires), _ptr(ib), ib.size, int(out_bits)))
+
     def load_npz(self, path):
         d = np.load(path)
         self.load_netlist(d["kind"], d["in0"], d["in1"], d["out"], int(d["n_wires"]), d["in_bits"], int(d["out_bits"]))
@@ -393,6 +410,37 @@ class Circuit:
         v = [C.c_uint32() for _ in range(6)]
         self._ck(self.L.bfhe_circuit_dump_gate_count(self.h, *[C.byref(x) for x in v]))
         return dict(zip(("input", "output", "and", "or", "xor", "not"), [x.value for x in v]))
+
+    def dumpGateCountEx(self):
+        v = (C.c_uint32 * 8)()
+        self._ck(self.L.bfhe_circuit_dump_gate_count_ex(self.h, v))
+        return dict(zip(("dff", "lut3", "lut4", "nand", "nor", "xnor", "xor_fast", "xnor_fast"), list(v)))
+
+    def _dump_text(self, what):
+        need = C.c_size_t()
+        self._ck(self.L.bfhe_circuit_dump_text(self.h, what, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value + 1)
+        self._ck(self.L.bfhe_circuit_dump_text(self.h, what, buf, need.value + 1, C.byref(need)))
+        return buf.value.decode()
+
+    def dumpNetList(self):
+        """text of Circuit::dumpNetList (src/circuit.cpp:844-855)"""
+        return self._dump_text(0)
+
+    def dumpGates(self):
+        """text of Circuit::dumpGates (src/circuit.cpp:856-865)"""
+        return self._dump_text(1)
+
+    def dff_plan(self):
+        n = C.c_uint32()
+        self._ck(self.L.bfhe_circuit_dff_plan(self.h, C.byref(n), None, 0))
+        q = np.zeros((n.value, 4), dtype=np.uint32)
+        if n.value:
+            self._ck(self.L.bfhe_circuit_dff_plan(self.h, C.byref(n), _ptr(q), n.value))
+        return q
+
+    def set_shard_threshold(self, min_bootstraps):
+        self._ck(self.L.bfhe_circuit_set_shard_threshold(self.h, min_bootstraps))
 
     def _push_flags(self):
         self._ck(self.L.bfhe_circuit_set_flags(self.h, *[int(f) for f in self._flags]))

@@ -24,6 +24,14 @@ int cuda_fail(cudaError_t e, const char *what) {
 extern "C" const char *bfhe_last_error(void) { return g_err.c_str(); }
 
 static constexpr double SIGMA = 3.19;
+static const GaussTable &gauss_table() {
+  static const GaussTable t(SIGMA);
+  return t;
+}
+static int make_seed_key(uint64_t seed, SeedKey &key) {
+  if (!SeedKey::make(seed, key)) { set_error("cannot read OS entropy (getrandom and /dev/urandom both failed)"); return BFHE_ERR_IO; }
+  return BFHE_OK;
+}
 
 // ---- key blob header (documented in include/bfhe.h / DESIGN.md) ----
 struct KeyBlobHeader {
@@ -225,7 +233,9 @@ extern "C" int bfhe_sync(bfhe_ctx *c) {
 // -------------------------------------------------------------------------------------------------
 extern "C" int bfhe_keygen(bfhe_ctx *c, uint64_t seed) {
   if (!c) return BFHE_ERR_ARG;
-  Rng r(seed, 0x5EC2E7);
+  SeedKey key;
+  if (int rc = make_seed_key(seed, key)) return rc;
+  Rng r(key, 0x5EC2E7);
   c->sk.resize(c->p.n);
   for (auto &s : c->sk) s = r.ternary();
   c->has_sk = true;
@@ -240,7 +250,7 @@ static void ksk_put(bfhe_ctx *c, u64 idx, u32 v) {
 }
 
 // one RGSW ciphertext of sign * X^mm (or of 0) under z, coefficient form: rows (a, a*z + e) + m*G
-static void rgsw_encrypt(const bfhe_ctx *c, const std::vector<u32> &z_eval, bool msg, u32 mm, int sign, u64 seed, u64 stream,
+static void rgsw_encrypt(const bfhe_ctx *c, const std::vector<u32> &z_eval, bool msg, u32 mm, int sign, const SeedKey &seed, u64 stream,
                          u32 *out) {
   const u32 N = c->p.N, rows = 2 * c->p.dG;
   const u32 Q = (u32)c->p.Q;
@@ -255,7 +265,7 @@ static void rgsw_encrypt(const bfhe_ctx *c, const std::vector<u32> &z_eval, bool
     for (u32 j = 0; j < N; j++) tmp[j] = (u32)((u64)tmp[j] * z_eval[j] % Q);
     c->hntt.inv(tmp.data());
     for (u32 j = 0; j < N; j++) {
-      i64 e = r.gauss(SIGMA);
+      i64 e = gauss_table().sample(r);
       b[j] = (u32)(((i64)tmp[j] + e + Q) % Q);
     }
     if (msg) {
@@ -267,13 +277,15 @@ static void rgsw_encrypt(const bfhe_ctx *c, const std::vector<u32> &z_eval, bool
   }
 }
 
-extern "C" int bfhe_btkeygen(bfhe_ctx *c, uint64_t seed) {
+extern "C" int bfhe_btkeygen(bfhe_ctx *c, uint64_t seed64) {
   if (!c) return BFHE_ERR_ARG;
   if (!c->has_sk) { set_error("BTKeyGen before KeyGen"); return BFHE_ERR_STATE; }
   const bfhe_params &p = c->p;
   const u32 n = p.n, N = p.N;
   const u32 Q = (u32)p.Q;
   const u64 qKS = p.qKS;
+  SeedKey seed;
+  if (int rc = make_seed_key(seed64, seed)) return rc;
   Rng rz(seed, 0x2A11);
   c->z.resize(N);
   for (auto &v : c->z) v = rz.ternary();
@@ -290,7 +302,7 @@ extern "C" int bfhe_btkeygen(bfhe_ctx *c, uint64_t seed) {
     for (u32 j = 0; j < p.baseKS; j++)
       for (u32 k = 0; k < p.dKS; k++) {
         const u64 base = (((u64)i * p.baseKS + j) * p.dKS + k) * (n + 1);
-        i64 b = r.gauss(SIGMA) + (i64)c->z[i] * (i64)((u64)j * Bpow[k] % qKS);
+        i64 b = gauss_table().sample(r) + (i64)c->z[i] * (i64)((u64)j * Bpow[k] % qKS);
         for (u32 t = 0; t < n; t++) {
           u64 a = r.uniform(qKS);
           ksk_put(c, base + t, (u32)a);
@@ -474,11 +486,13 @@ extern "C" int bfhe_encrypt(const bfhe_ctx *c, const uint8_t *bits, size_t count
   if (!c || !bits || !ct) return BFHE_ERR_ARG;
   if (!c->has_sk) { set_error("Encrypt before KeyGen"); return BFHE_ERR_STATE; }
   const u32 n = c->p.n, q = c->p.q, stride = c->p.ct_stride;
+  SeedKey key;
+  if (int rc = make_seed_key(seed, key)) return rc;
 #pragma omp parallel for schedule(static) if (count > 256)
   for (i64 g = 0; g < (i64)count; g++) {
-    Rng r(seed, 0x900000 + (u64)g);
+    Rng r(key, 0x900000 + (u64)g);
     u32 *row = ct + (size_t)g * stride;
-    i64 b = (i64)(bits[g] % 4) * (q / 4) + r.gauss(SIGMA);
+    i64 b = (i64)(bits[g] % 4) * (q / 4) + gauss_table().sample(r);
     for (u32 i = 0; i < n; i++) {
       row[i] = (u32)r.uniform(q);
       b += (i64)row[i] * c->sk[i];

@@ -69,6 +69,10 @@ struct bfhe_ctx {
   bfhe::u32 *e2e_slab = nullptr;
   size_t e2e_rows = 0;
   int force_g = 0; // test hook: gates per CTA
+  // measured cost (ms) of one wave (blind rotation + key switch) in the 4-CTA / 2-CTA cluster, one-gate-per-SM and four-gates-per-SM
+  // forms on this device with this key set (host/circuit.cpp probe_costs)
+  double form_cost_ms[4] = {0, 0, 0, 0};
+  bool form_cost_measured = false;
 
   bool profiling = false;
   std::vector<bfhe::ProfSpan> spans;

@@ -4,6 +4,8 @@
 #pragma once
 #include "common.hpp"
 #include <cmath>
+#include <cstdio>
+#include <sys/random.h>
 #include <vector>
 
 namespace bfhe {
@@ -87,32 +89,111 @@ inline int ilog2_ceil(u64 x) {
   return l;
 }
 
-// counter-seeded xoshiro256**: every key row gets its own stream, so key generation is
-// deterministic for a seed regardless of the OpenMP thread count.
-struct Rng {
-  u64 s[4];
-  static u64 splitmix(u64 &x) {
-    u64 z = (x += 0x9E3779B97F4A7C15ull);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+// ---- randomness ------------------------------------------------------------------------------------------------------
+// Secret keys, RGSW / key-switching keys and fresh-encryption masks and noise come from ChaCha20 (RFC 8439 block function)
+// keyed with a 256-bit SeedKey; every key row / ciphertext gets its own 64-bit stream id (the ChaCha nonce), so generation is
+// deterministic for a SeedKey regardless of the OpenMP thread count.
+//   seed == 0  -> the SeedKey is 256 bits of OS entropy (getrandom / /dev/urandom): the default, and the only secure choice
+//   seed != 0  -> the SeedKey is derived from the 64-bit seed alone: reproducible keys and ciphertexts for tests, oracle parity
+//                 and benchmarks; NOT confidential (2^64 search space, and the seeds in the tests are public)
+// (the reference draws from OpenFHE's PRNG, which seeds itself from the OS; include/bfhe.h states this contract)
+struct SeedKey {
+  u32 k[8];
+  static bool os_entropy(void *buf, size_t len) {
+    u8 *p = (u8 *)buf;
+    size_t got = 0;
+    while (got < len) {
+      ssize_t r = getrandom(p + got, len - got, 0);
+      if (r <= 0) break;
+      got += (size_t)r;
+    }
+    if (got == len) return true;
+    FILE *f = std::fopen("/dev/urandom", "rb");
+    if (!f) return false;
+    const size_t rd = std::fread(p, 1, len, f);
+    std::fclose(f);
+    return rd == len;
   }
-  Rng(u64 seed, u64 stream) {
-    u64 x = seed ^ (stream * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull);
-    for (auto &v : s) v = splitmix(x);
+  static bool make(u64 seed, SeedKey &out) {
+    if (seed == 0) return os_entropy(out.k, sizeof out.k);
+    u64 x = seed; // splitmix64 expansion of the test seed into the key words (domain separation only, not security)
+    for (int i = 0; i < 4; i++) {
+      u64 z = (x += 0x9E3779B97F4A7C15ull);
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      out.k[2 * i] = (u32)z; out.k[2 * i + 1] = (u32)(z >> 32);
+    }
+    return true;
   }
-  static u64 rotl(u64 x, int k) { return (x << k) | (x >> (64 - k)); }
-  u64 next() {
-    u64 res = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
-    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
-    return res;
+};
+
+struct Rng { // ChaCha20 keystream: key = SeedKey, nonce = stream id, 64-bit block counter
+  u32 st[16], buf[16];
+  int pos = 16;
+  Rng(const SeedKey &key, u64 stream) {
+    st[0] = 0x61707865u; st[1] = 0x3320646eu; st[2] = 0x79622d32u; st[3] = 0x6b206574u;
+    for (int i = 0; i < 8; i++) st[4 + i] = key.k[i];
+    st[12] = 0; st[13] = 0;
+    st[14] = (u32)stream; st[15] = (u32)(stream >> 32);
   }
-  u64 uniform(u64 m) { return next() % m; }
-  int ternary() { return (int)(next() % 3) - 1; }
-  i64 gauss(double sigma) {
-    double u1 = ((next() >> 11) + 1.0) / 9007199254740993.0;
-    double u2 = (next() >> 11) / 9007199254740992.0;
-    return llround(sigma * std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2));
+  static u32 rotl(u32 x, int k) { return (x << k) | (x >> (32 - k)); }
+  void refill() {
+    u32 x[16];
+    for (int i = 0; i < 16; i++) x[i] = st[i];
+#define BFHE_QR(a, b, c, d)                                                                                            \
+  x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12);                              \
+  x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
+    for (int r = 0; r < 10; r++) {
+      BFHE_QR(0, 4, 8, 12) BFHE_QR(1, 5, 9, 13) BFHE_QR(2, 6, 10, 14) BFHE_QR(3, 7, 11, 15)
+      BFHE_QR(0, 5, 10, 15) BFHE_QR(1, 6, 11, 12) BFHE_QR(2, 7, 8, 13) BFHE_QR(3, 4, 9, 14)
+    }
+#undef BFHE_QR
+    for (int i = 0; i < 16; i++) buf[i] = x[i] + st[i];
+    if (++st[12] == 0) ++st[13];
+    pos = 0;
+  }
+  u32 next32() {
+    if (pos >= 16) refill();
+    return buf[pos++];
+  }
+  u64 next() { const u64 lo = next32(); return lo | ((u64)next32() << 32); }
+  u64 uniform(u64 m) { // unbiased: rejection sampling on the smallest covering power of two
+    if (m <= 1) return 0;
+    const int bits = ilog2_ceil(m);
+    const u64 mask = bits >= 64 ? ~0ull : (((u64)1 << bits) - 1);
+    for (;;) {
+      const u64 v = (bits <= 32 ? (u64)next32() : next()) & mask;
+      if (v < m) return v;
+    }
+  }
+  int ternary() { return (int)uniform(3) - 1; }
+};
+
+// discrete Gaussian by inversion of a cumulative table (what OpenFHE's DiscreteGaussianGenerator does for small sigma):
+// P(|x| = k) proportional to exp(-k^2 / (2 sigma^2)), tail cut at 12 sigma (mass < 2^-100), 64-bit uniform draw
+struct GaussTable {
+  std::vector<u64> cdf; // cdf[k] = floor(2^64 * P(|x| <= k)) for k >= 0, saturating
+  explicit GaussTable(double sigma) {
+    const int kmax = (int)std::ceil(12 * sigma);
+    std::vector<long double> w(kmax + 1);
+    long double tot = 0;
+    for (int k = 0; k <= kmax; k++) { w[k] = std::exp(-(long double)k * k / (2.0L * sigma * sigma)) * (k ? 2.0L : 1.0L); tot += w[k]; }
+    long double acc = 0;
+    cdf.resize(kmax + 1);
+    for (int k = 0; k <= kmax; k++) {
+      acc += w[k] / tot;
+      const long double v = acc * 18446744073709551616.0L;
+      cdf[k] = v >= 18446744073709551615.0L ? ~0ull : (u64)v;
+    }
+    cdf[kmax] = ~0ull;
+  }
+  i64 sample(Rng &r) const {
+    const u64 u = r.next();
+    size_t k = 0;
+    while (k + 1 < cdf.size() && u > cdf[k]) k++;
+    if (k == 0) return 0;
+    return (r.next32() & 1) ? (i64)k : -(i64)k;
   }
 };
 

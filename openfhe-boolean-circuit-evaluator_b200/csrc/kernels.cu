@@ -26,6 +26,14 @@
 
 namespace bfhe {
 
+// cudaFuncSetAttribute is per DEVICE: one process may hold contexts on several GPUs, so the "already done" flags of the launch
+// helpers below are kept per device ordinal
+static inline int attr_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < 64 ? dev : 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // modular arithmetic
 // ------------------------------------------------------------------------------------------
@@ -1105,11 +1113,11 @@ static int launch_lat_inst(const DevConst &P, const DevGate *d_gates, int count,
                            const u32 *d_psiM, u32 *d_ext, u32 *d_acc, cudaStream_t st, LaunchInfo *info) {
   using Cfg = LatCfg<LOGN, DG, LOGBG, AP>;
   auto kern = blind_rotate_lat_kernel<LOGN, DG, LOGBG, AP>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64];
+  if (!attr_done[attr_device_slot()]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done[attr_device_slot()] = true;
   }
   if (count <= 0) return 0;
   if (info) { info->gates_per_cta = 1; info->ctas = count; info->smem_bytes = Cfg::smem_bytes; }
@@ -1122,11 +1130,11 @@ static int launch_br_inst(const DevConst &P, const DevGate *d_gates, int count, 
                           const u32 *d_psiM, u32 *d_ext, u32 *d_acc, cudaStream_t st, LaunchInfo *info) {
   using Cfg = BrCfg<LOGN, DG, LOGBG, G, AP>;
   auto kern = blind_rotate_kernel<LOGN, DG, LOGBG, G, AP>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64];
+  if (!attr_done[attr_device_slot()]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done[attr_device_slot()] = true;
   }
   if (count <= 0) return 0; // attribute warm-up only
   const int ctas = (count + G - 1) / G;
@@ -1356,8 +1364,8 @@ int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates
     constexpr int COLS = 256, RG = 4;
     const int rowlen_words = 256; // 512 uint16 per row
     size_t smem = (size_t)((nrows + 1) & ~1) * 4 + (size_t)RG * COLS * 2 * 8;
-    static bool done = false;
-    if (!done) { keyswitch_attrs(); done = true; }
+    static bool done[64];
+    if (!done[attr_device_slot()]) { keyswitch_attrs(); done[attr_device_slot()] = true; }
     // while every CTA of the cluster form has an SM to itself it wins (measured: 1 gate 47 -> 23 us, 30 gates 56 -> 29 us; 74 gates
     // 57 -> 54 us; 148 gates 56 -> 82 us): used up to SMs / 4 gates, wider batches keep one CTA per gate
     int dev = 0, sms = 148;
@@ -1380,11 +1388,14 @@ int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates
 // ------------------------------------------------------------------------------------------
 // EvalNOT (a6): (-a, q/4 - b)
 // ------------------------------------------------------------------------------------------
+// low bit of the (16-byte aligned) input pointer set: plain copy of the ciphertext (DFF state moves of clocked circuits)
 __global__ void eval_not_kernel(const __grid_constant__ DevConst P, const u32 *const *__restrict__ in, u32 *const *__restrict__ out) {
-  const u32 *x = in[blockIdx.x];
+  const uintptr_t raw = reinterpret_cast<uintptr_t>(in[blockIdx.x]);
+  const u32 *x = reinterpret_cast<const u32 *>(raw & ~(uintptr_t)15);
+  const bool copy = raw & 1;
   u32 *y = out[blockIdx.x];
   const u32 q = P.q, n = P.n;
-  for (u32 i = threadIdx.x; i <= n; i += blockDim.x) y[i] = (i == n) ? (q / 4 + q - x[i]) % q : (q - x[i]) % q;
+  for (u32 i = threadIdx.x; i <= n; i += blockDim.x) y[i] = copy ? x[i] : (i == n) ? (q / 4 + q - x[i]) % q : (q - x[i]) % q;
 }
 int launch_eval_not(const DevConst &P, const u32 *const *d_in, u32 *const *d_out, int count, void *stream) {
   if (count <= 0) return 0;

@@ -50,11 +50,13 @@ public:
     m_ctx.reset(c, bfhe_destroy);
     bfhe_get_params(c, &m_p);
   }
-  LWEPrivateKey KeyGen(uint64_t seed = 0x5eed) const {
+  // seed == 0 (default): keys, masks and noise are drawn from a ChaCha20 stream keyed with 256 bits of OS entropy, like OpenFHE's
+  // self-seeding PRNG.  A non-zero seed gives reproducible (and therefore NOT confidential) material for tests and parity runs.
+  LWEPrivateKey KeyGen(uint64_t seed = 0) const {
     check(bfhe_keygen(raw(), seed));
     return std::make_shared<LWEPrivateKeyImpl>();
   }
-  void BTKeyGen(ConstLWEPrivateKey, uint64_t seed = 0xb7) { check(bfhe_btkeygen(raw(), seed)); }
+  void BTKeyGen(ConstLWEPrivateKey, uint64_t seed = 0) { check(bfhe_btkeygen(raw(), seed)); }
   LWECiphertext Encrypt(ConstLWEPrivateKey, const LWEPlaintext &m, BINFHE_OUTPUT output = BOOTSTRAPPED) const {
     auto ct = std::make_shared<LWECiphertextImpl>();
     ct->row.resize(m_p.ct_stride);
@@ -81,13 +83,19 @@ public:
   }
   const bfhe_params &params() const { return m_p; }
   void SetBootstrapFreshEncryptions(bool on) { m_bootstrap_inputs = on; }
+  void SetEncryptionSeed(uint64_t seed) { m_seed = seed; }
 
 private:
   static void check(int rc) {
     if (rc == BFHE_ERR_ALIAS) throw config_error(bfhe_last_error());
     if (rc != BFHE_OK) throw std::runtime_error(bfhe_last_error());
   }
-  uint64_t next_seed() const { return m_seed = m_seed * 6364136223846793005ull + 1442695040888963407ull; }
+  // 0 = OS entropy for every encryption (default); SetEncryptionSeed(s != 0) = reproducible sequence for tests
+  uint64_t next_seed() const {
+    if (m_seed == 0) return 0;
+    m_seed = m_seed * 6364136223846793005ull + 1442695040888963407ull;
+    return m_seed ? m_seed : 1;
+  }
   LWECiphertext one_gate(uint32_t op, ConstLWECiphertext a, ConstLWECiphertext b) const {
     const size_t st = m_p.ct_stride;
     auto out = std::make_shared<LWECiphertextImpl>();
@@ -113,7 +121,7 @@ private:
   std::shared_ptr<bfhe_ctx> m_ctx;
   bfhe_params m_p{};
   bool m_bootstrap_inputs = true;
-  mutable uint64_t m_seed = 0x243f6a8885a308d3ull;
+  mutable uint64_t m_seed = 0;
 };
 
 } // namespace lbcrypto

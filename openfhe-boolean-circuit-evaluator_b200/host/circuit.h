@@ -47,7 +47,8 @@ private:
 
 class Circuit {
 public:
-  Circuit(lbcrypto::BINFHE_PARAMSET set, lbcrypto::BINFHE_METHOD method, int device = 0, uint64_t key_seed = 1) {
+  // key_seed == 0 (default): keys and input encryptions from OS entropy; non-zero: reproducible, for tests only
+  Circuit(lbcrypto::BINFHE_PARAMSET set, lbcrypto::BINFHE_METHOD method, int device = 0, uint64_t key_seed = 0) {
     // only TOY / STD128_OPT and AP / GINX, otherwise exit(-1), as src/circuit.cpp:69-86
     if (set != lbcrypto::TOY && set != lbcrypto::STD128_OPT) {
       std::cerr << "bad paramset" << std::endl;
@@ -59,7 +60,8 @@ public:
     }
     cc.GenerateBinFHEContext(set, method, device); // src/circuit.cpp:88
     sk = cc.KeyGen(key_seed);                      // :90
-    cc.BTKeyGen(sk, key_seed + 1);                 // :91
+    cc.BTKeyGen(sk, key_seed ? key_seed + 1 : 0);  // :91
+    input_seed = key_seed ? key_seed + 2 : 0;
     gep.cc = cc;                                   // shares keys, :93-97
     gep.sk = sk;
     h = bfhe_circuit_create(cc.raw());
@@ -84,7 +86,7 @@ public:
       if (verbose) std::cout << "setting input size " << bus.size() << std::endl;
       for (auto b : bus) flat.push_back((uint8_t)b);
     }
-    ok(bfhe_circuit_set_input(h, flat.data(), flat.size(), input_seed++));
+    ok(bfhe_circuit_set_input(h, flat.data(), flat.size(), input_seed ? input_seed++ : 0));
   }
   void setPlaintext(bool f) { plaintext_flag = f; push_flags(); }
   bool getPlaintext() const { return plaintext_flag; }
@@ -115,10 +117,12 @@ public:
   void dumpGateCount() {
     uint32_t i, o, a, r, x, n;
     bfhe_circuit_dump_gate_count(h, &i, &o, &a, &r, &x, &n);
-    std::cout << "Gate count: input " << i << " output " << o << " and " << a << " or " << r << " xor " << x << " not " << n << std::endl;
+    // the reference's wording and order, src/circuit.cpp:866-873
+    std::cout << "Number of input gates " << i << std::endl << "Number of output gates " << o << std::endl << "Number of not gates " << n << std::endl
+              << "Number of and gates " << a << std::endl << "Number of or gates " << r << std::endl << "Number of xor gates " << x << std::endl;
   }
-  void dumpNetList() { dumpGateCount(); }
-  void dumpGates() { dumpGateCount(); }
+  void dumpNetList() { std::cout << dump_text(0); } // src/circuit.cpp:844-855
+  void dumpGates() { std::cout << dump_text(1); }   // src/circuit.cpp:856-865
   uint64_t verifyMismatches() const {
     uint64_t bad = 0;
     bfhe_circuit_stats(h, nullptr, nullptr, &bad);
@@ -128,6 +132,14 @@ public:
   Outputs plainOut;
 
 private:
+  std::string dump_text(int what) {
+    size_t need = 0;
+    if (bfhe_circuit_dump_text(h, what, nullptr, 0, &need) != BFHE_OK) return std::string();
+    std::string s(need + 1, '\0');
+    bfhe_circuit_dump_text(h, what, &s[0], s.size(), &need);
+    s.resize(need);
+    return s;
+  }
   bool ok(int rc) {
     if (rc != BFHE_OK) std::cerr << bfhe_last_error() << std::endl;
     return rc == BFHE_OK;
@@ -138,5 +150,5 @@ private:
   bool plaintext_flag = false, encrypted_flag = false, verify_flag = false;
   GateEvalParams gep;
   bfhe_circuit *h = nullptr;
-  uint64_t input_seed = 1;
+  uint64_t input_seed = 0;
 };
