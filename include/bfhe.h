@@ -160,6 +160,10 @@ int bfhe_circuit_reset(bfhe_circuit *);                                     /* C
 int bfhe_circuit_set_input(bfhe_circuit *, const uint8_t *bits, size_t nbits, uint64_t seed); /* Circuit::SetInput (all input buses concatenated) */
 int bfhe_circuit_clock(bfhe_circuit *, uint8_t *out_bits, size_t cap, uint8_t *plain_out_bits); /* Circuit::Clock */
 int bfhe_circuit_stats(const bfhe_circuit *, double *device_ms, double *host_ms, uint64_t *verify_mismatches);
+/* the schedule in use: wave capacity (0 = ASAP), levels incl. the input-bootstrap level, levels that are sharded, and the four launch
+ * costs (ms: 4-CTA cluster, 2-CTA cluster, one gate per SM, four gates per SM) the planner used -- measured by a start-up probe on the
+ * first encrypted SetInput when the capacity is left to the cost model */
+int bfhe_circuit_get_schedule(const bfhe_circuit *, uint32_t *wave_cap, uint32_t *n_levels, uint32_t *n_sharded, double *cost_ms4);
 /* per-level plan, for tests of the sharding logic: gates of level L assigned to `rank` of `world`; *rows_per_rank == 0 with
  * world > 1 means the level is not sharded (every rank evaluates all of it, no exchange follows) */
 int bfhe_circuit_level_plan(const bfhe_circuit *, uint32_t level, int rank, int world, bfhe_gate *out, size_t cap,

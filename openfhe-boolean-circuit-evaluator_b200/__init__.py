@@ -55,7 +55,7 @@ ABI_SYMBOLS = [
     "bfhe_circuit_level_plan", "bfhe_circuit_plan_misc", "bfhe_circuit_use_graph", "bfhe_circuit_download_slab",
     "bfhe_circuit_dump_gate_count", "bfhe_circuit_load_netlist", "bfhe_circuit_get_netlist", "bfhe_circuit_write_out",
     "bfhe_circuit_load_netlist_ex", "bfhe_circuit_set_shard_threshold", "bfhe_circuit_dump_gate_count_ex",
-    "bfhe_circuit_dump_text", "bfhe_circuit_dff_plan",
+    "bfhe_circuit_dump_text", "bfhe_circuit_dff_plan", "bfhe_circuit_get_schedule",
 ]
 
 _lib = None
@@ -131,6 +131,7 @@ def lib():
     L.bfhe_circuit_dump_gate_count_ex.argtypes = [vp, u32p]
     L.bfhe_circuit_dump_text.argtypes = [vp, C.c_int, C.c_char_p, sz, C.POINTER(sz)]
     L.bfhe_circuit_dff_plan.argtypes = [vp, u32p, vp, sz]
+    L.bfhe_circuit_get_schedule.argtypes = [vp, u32p, u32p, u32p, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -343,6 +344,7 @@ class Circuit:
         self.ctx, self.L = ctx, ctx.L
         self.h = self.L.bfhe_circuit_create(ctx.h)
         self._flags = [False, False, False]
+        self.world_size = 1
 
     def close(self):
         if getattr(self, "h", None):
@@ -439,6 +441,12 @@ class Circuit:
             self._ck(self.L.bfhe_circuit_dff_plan(self.h, C.byref(n), _ptr(q), n.value))
         return q
 
+    def schedule(self):
+        cap, nl, ns = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        cost = (C.c_double * 4)()
+        self._ck(self.L.bfhe_circuit_get_schedule(self.h, C.byref(cap), C.byref(nl), C.byref(ns), cost))
+        return dict(wave_cap=cap.value, n_levels=nl.value, n_sharded=ns.value, cost_ms=dict(zip(("cl4", "cl2", "lat", "thr"), list(cost))))
+
     def set_shard_threshold(self, min_bootstraps):
         self._ck(self.L.bfhe_circuit_set_shard_threshold(self.h, min_bootstraps))
 
@@ -479,6 +487,7 @@ class Circuit:
 
     def set_sharding(self, rank, world, unique_id=None):
         self._ck(self.L.bfhe_circuit_set_sharding(self.h, rank, world, _ptr(unique_id)))
+        self.world_size = world
 
     def use_graph(self, on):
         self._ck(self.L.bfhe_circuit_use_graph(self.h, int(on)))

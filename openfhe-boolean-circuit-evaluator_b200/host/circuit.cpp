@@ -971,6 +971,17 @@ extern "C" int bfhe_circuit_set_shard_threshold(bfhe_circuit *c, int min_bootstr
   if (c->loaded) return replan(c);
   return BFHE_OK;
 }
+/* the schedule the planner chose: wave capacity (0 = ASAP levels), number of levels incl. the input level, how many of them are sharded */
+extern "C" int bfhe_circuit_get_schedule(const bfhe_circuit *c, uint32_t *wave_cap, uint32_t *n_levels, uint32_t *n_sharded, double *cost_ms4) {
+  if (!c || !c->planned) return BFHE_ERR_STATE;
+  if (wave_cap) *wave_cap = c->wave_cap;
+  if (n_levels) *n_levels = (uint32_t)c->levels.size();
+  uint32_t ns = 0;
+  for (const Level &l : c->levels) ns += (c->world > 1 && l.sharded && !l.gates.empty()) ? 1 : 0;
+  if (n_sharded) *n_sharded = ns;
+  if (cost_ms4) { cost_ms4[0] = c->costs.cl4; cost_ms4[1] = c->costs.cl2; cost_ms4[2] = c->costs.lat; cost_ms4[3] = c->costs.thr; }
+  return BFHE_OK;
+}
 extern "C" int bfhe_circuit_level_plan(const bfhe_circuit *c, uint32_t level, int rank, int world, bfhe_gate *out, size_t cap,
                                        uint32_t *count, uint32_t *first_row, uint32_t *rows_per_rank) {
   if (!c || !c->planned || level >= c->levels.size()) return BFHE_ERR_ARG;

@@ -91,6 +91,117 @@ def test_config5_aes128(bfhe):
     assert np.array_equal(slab_graph, c.download_slab())
 
 
+def test_config5_aes128_expanded(bfhe):
+    """old-bristol AES-128 with the expanded key as input 2 (src/test_aes.cpp:187-202): both KATs, encrypted."""
+    ctx = shared_keys(bfhe, bfhe.STD128_OPT, bfhe.GINX, 0)
+    c = load_circuit(bfhe, ctx, "AES-expanded")
+    for t, v in enumerate(VECTORS["AES-expanded"]["vectors"]):
+        assert _run_encrypted(c, v, seed=20 + t, verify=False) == v["golden"], v["src"]
+
+
+def test_config5_md5(bfhe):
+    """old-bristol MD5, the four KATs of src/test_md5.cpp:203-228, encrypted (71 534 bootstraps in 3 852 levels each)."""
+    ctx = shared_keys(bfhe, bfhe.STD128_OPT, bfhe.GINX, 0)
+    c = load_circuit(bfhe, ctx, "md5")
+    for t, v in enumerate(VECTORS["md5"]["vectors"]):
+        assert _run_encrypted(c, v, seed=30 + t, verify=(t == 0)) == v["golden"], v["src"]
+        assert c.stats()["verify_mismatches"] == 0
+
+
+def test_config5_sha256(bfhe):
+    """SHA-256 (new-bristol sha256.txt, IV as input 2), the four KATs of src/test_sha256.cpp:205-238, encrypted
+    (354 505 bootstraps in 9 055 levels each: the slow test of the suite)."""
+    ctx = shared_keys(bfhe, bfhe.STD128_OPT, bfhe.GINX, 0)
+    c = load_circuit(bfhe, ctx, "sha256")
+    for t, v in enumerate(VECTORS["sha256"]["vectors"]):
+        assert _run_encrypted(c, v, seed=40 + t, verify=False) == v["golden"], v["src"]
+
+
+EXT_OUT = """R0 = LOAD(In1,0)
+R1 = LOAD(In1,1)
+R2 = LOAD(In1,2)
+R3 = NAND(R0, R1)
+R4 = NOR(R1, R2)
+R5 = XNOR(R3, R4)
+R6 = XOR_FAST(R5, R0)
+R7 = XNOR_FAST(R6, R2)
+R8 = LUT3(R0, R1, R2, 0xE8)
+R9 = NOT(R8)
+R10 = NOT(R9)
+R11 = NOT(R10)
+R12 = AND(R10, R7)
+Out0 = STORE(R3)
+Out1 = STORE(R5)
+Out2 = STORE(R7)
+Out3 = STORE(R8)
+Out4 = STORE(R9)
+Out5 = STORE(R10)
+Out6 = STORE(R11)
+Out7 = STORE(R12)
+"""
+
+
+@pytest.mark.parametrize("ps,m", [("STD128_OPT", "GINX"), ("TOY", "AP")])
+def test_extended_gate_kinds_and_not_chains(bfhe, orc, tmp_path, ps, m):
+    """Rows f-4 + ADVICE: native NAND / NOR / XOR_FAST / XNOR_FAST, composite XNOR, a lowered LUT3 and a NOT-NOT-NOT chain feeding
+    outputs, encrypted with gate-by-gate verify; every wire ciphertext equals the oracle executing the same plan."""
+    import itertools
+    ctx = shared_keys(bfhe, getattr(bfhe, ps), getattr(bfhe, m), 0)
+    p = tmp_path / "ext.out"
+    p.write_text(EXT_OUT)
+    c = bfhe.Circuit(ctx)
+    c.ReadFile(p)
+    for t, (a, b, d) in enumerate(itertools.product((0, 1), repeat=3)):
+        n3, n4 = 1 - (a & b), 1 - (b | d)
+        r5 = 1 - (n3 ^ n4)
+        r7 = 1 - ((r5 ^ a) ^ d)
+        maj = int(a + b + d >= 2)
+        want = [n3, r5, r7, maj, 1 - maj, maj, 1 - maj, maj & r7]
+        for verify in (True, False):
+            assert _run_encrypted(c, {"inputs": [[a, b, d]]}, seed=50 + t, verify=verify) == want, (a, b, d, verify)
+            assert c.stats()["verify_mismatches"] == 0
+    o = orc.Oracle(getattr(orc, ps), getattr(orc, m))
+    o.import_keys(ctx.export_keys())
+    for verify in (True, False):
+        _run_encrypted(c, {"inputs": [[1, 0, 1]]}, seed=77, verify=verify)
+        slab = c.download_slab()
+        fresh = ctx.encrypt([1, 0, 1], seed=77)
+        _, ref = oracle_run_plan(c, o, [[1, 0, 1]], fresh=fresh)
+        w = ctx.p.ct_words
+        assert np.array_equal(slab[:, :w], ref[:, :w]), verify
+
+
+COUNTER = """R0 = LOAD(In1,0)
+R1 = DFF(R5)
+R2 = DFF(R6)
+R5 = XOR(R1, R0)
+R3 = AND(R1, R0)
+R6 = XOR(R2, R3)
+Out0 = STORE(R1)
+Out1 = STORE(R2)
+"""
+
+
+@pytest.mark.parametrize("ps,graph", [("TOY", True), ("STD128_OPT", True), ("TOY", False)])
+def test_dff_counter_encrypted(bfhe, tmp_path, ps, graph):
+    """Clocked circuit on the GPU: a 2-bit counter with enable, six Clock() calls on one SetInput, then a hold, then Reset; verify mode
+    checks every wire (the Q rows included) on every clock."""
+    ctx = shared_keys(bfhe, getattr(bfhe, ps), bfhe.GINX, 0)
+    p = tmp_path / "counter.out"
+    p.write_text(COUNTER)
+    c = bfhe.Circuit(ctx)
+    c.ReadFile(p)
+    c.use_graph(graph)
+    for verify in (True, False):
+        c.Reset(); c.setEncrypted(True); c.setVerify(verify)
+        c.SetInput([[1]], seed=5)
+        seen = [c.Clock()[0] for _ in range(6)]
+        assert seen == [[0, 0], [1, 0], [0, 1], [1, 1], [0, 0], [1, 0]], (verify, seen)
+        c.SetInput([[0]], seed=6)
+        assert c.Clock()[0] == [0, 1] and c.Clock()[0] == [0, 1]
+        assert c.stats()["verify_mismatches"] == 0
+
+
 def test_out_file_path_on_gpu(bfhe, tmp_path):
     """ReadFile('.out') -> encrypted Clock, the reference's own entry path (src/test_adder.cpp:155-156)."""
     ctx = shared_keys(bfhe, bfhe.TOY, bfhe.GINX, 0)

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, nvec, q, cap=0):
+def _worker(rank, world, port, name, nvec, q, cap=0, thr=-1):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import bfhe_loader
@@ -40,6 +40,11 @@ def _worker(rank, world, port, name, nvec, q, cap=0):
     circ = load_circuit(B, ctx, name)
     circ.set_sharding(rank, world)
     circ.set_wave_capacity(cap)  # 0 = the reference's ASAP waves; > 0 = packed waves (must be identical on every rank)
+    if thr >= 0:  # levels narrower than thr are evaluated redundantly by every rank and skip the exchange
+        circ.set_shard_threshold(thr)
+        widths = [len(circ.level_plan(L, rank, world)[0]) for L in range(circ.plan_misc()["n_levels"])]
+        unsharded = [L for L in range(len(widths)) if circ.level_plan(L, rank, world)[2] == 0 and widths[L]]
+        assert unsharded and len(unsharded) < len(widths), "the threshold must split the levels into both kinds"
 
     def gather(blk, r, rpr):
         mine = torch.from_numpy(np.ascontiguousarray(blk[r * rpr:(r + 1) * rpr]).astype(np.int32))
@@ -63,12 +68,12 @@ def _worker(rank, world, port, name, nvec, q, cap=0):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,nvec,cap", [("adder_2bit", 3, 0), ("parity", 2, 0), ("parity", 2, 4)])
-def test_world2_gloo_sharded_levels(name, nvec, cap):
+@pytest.mark.parametrize("name,nvec,cap,thr", [("adder_2bit", 3, 0, -1), ("parity", 2, 0, -1), ("parity", 2, 4, -1), ("adder_2bit", 2, 0, 4)])
+def test_world2_gloo_sharded_levels(name, nvec, cap, thr):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 200) + (0 if name == "adder_2bit" else 1) + 2 * (cap > 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, nvec, q, cap)) for r in range(2)]
+    port = 29600 + (os.getpid() % 200) + (0 if name == "adder_2bit" else 1) + 2 * (cap > 0) + 4 * (thr >= 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, nvec, q, cap, thr)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
