@@ -55,11 +55,14 @@ struct V2Bufs {
   const u32 *d_bk4 = nullptr; // the same, split [step][quarter of the slots][polynomial][N/4]: the 2-CTA and 4-CTA cluster kernels
   const u32 *d_tw2 = nullptr; // fwd w | fwd ws | inv w | inv ws, each N words (order: kernels_v2.cu Tabs)
   const u32 *d_F = nullptr;   // (psi^k - 1) * 2^32 mod Q, k < 2N
+  const u32 *d_bkx = nullptr; // slot-sliced 4-CTA cluster kernel (kernels_cl.cu): key as [step][rank][polynomial][N/4]
+  const u32 *d_twx = nullptr; // ... and its per-rank twiddle blocks
 };
 
 // kernels.cu entry points (all asynchronous on `stream`; return cudaError_t as int)
 // force_gates_per_cta: 0 = cost model; 1, 2, 4 = first-generation throughput form; 8 = latency form; 16 = second-generation
-// throughput form; 32 = cluster latency form (one gate on two SMs); 64 = one gate on four SMs
+// throughput form; 32 = cluster latency form (one gate on two SMs); 64 = one gate on four SMs (round-1 form); 128 = one gate on four SMs,
+// slot-sliced (kernels_cl.cu)
 int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates, int count, const u32 *d_bk,
                         const u32 *d_twl /*fwd w | fwd ws | inv w | inv ws, each N words*/, const u32 *d_psiM,
                         u32 *d_ext /*count * (N+4)*/, u32 *d_acc_dbg /*nullable: count*2*N*/, int force_gates_per_cta,
@@ -78,6 +81,14 @@ int launch_blind_rotate_v2(const DevConst &P, const DevGate *d_gates, int count,
                            void *stream, LaunchInfo *info);
 // one gate on a 2-CTA cluster (two SMs): the latency form for wavefronts narrower than half the SM count
 int launch_blind_rotate_cl2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
+                            void *stream, LaunchInfo *info);
+// kernels_cl.cu: one gate on a 4-CTA cluster, everything sliced by evaluation slot, one exchange per step
+bool clx_supported(const DevConst &P, int method_ap);
+size_t clx_tw_words();
+int clx_set_attrs();
+int clx_max_gates();
+int launch_bk_slice_clx(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
+int launch_blind_rotate_clx(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
                             void *stream, LaunchInfo *info);
 int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates, int count, const void *d_ksk,
                      int ksk_elem_bytes, void *stream);

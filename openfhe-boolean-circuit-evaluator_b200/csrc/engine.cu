@@ -175,6 +175,35 @@ extern "C" bfhe_ctx *bfhe_create(int paramset, int method, int device) {
            cudaMemcpy(c->d_F, F.data(), F.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
       c->v2.d_tw2 = c->d_tw2; c->v2.d_F = c->d_F;
     }
+    if (ok && clx_supported(P, method == BFHE_AP)) { // per-rank twiddle blocks of the slot-sliced cluster kernel (layout: kernels_cl.cu TWW)
+      // CTA k runs the sub-transform of block k (in-place positions 256 k + i, i < 256) as: pass A (lane holds i = lane + 32 m),
+      // pass B (lane = 4 blk + q holds i = 32 blk + q + 4 m), two stages across lanes.  A stage with G groups uses tw[G + group],
+      // group = position / (N / G) -- the table order of HostNtt (tw[k] = psi^bitrev(k)).
+      const size_t TWW = 8 + 3 * 256, TWP = (TWW + 3) & ~(size_t)3;
+      std::vector<u32> tx(clx_tw_words(), 0);
+      for (u32 k = 0; k < 4; k++)
+        for (int inv = 0; inv < 2; inv++) {
+          u32 *w = tx.data() + ((size_t)k * 4 + 2 * inv) * TWP, *ws = w + TWP;
+          auto put = [&](size_t off, u32 idx) {
+            const u32 v = inv ? c->hntt.itw[idx] : c->hntt.tw[idx];
+            w[off] = v; ws[off] = shoup32(v, Q);
+          };
+          put(1, 4 + k);
+          for (u32 g = 0; g < 2; g++) put(2 + g, 8 + 2 * k + g);
+          for (u32 g = 0; g < 4; g++) put(4 + g, 16 + 4 * k + g);
+          for (u32 lane = 0; lane < 32; lane++) {
+            const u32 blk = lane >> 2, q = lane & 3;
+            auto at = [&](int s, u32 e) { return 8 + 256 * (size_t)s + ((size_t)(e >> 2) * 32 + lane) * 4 + (e & 3); }; // [chunk][lane][4]
+            put(at(0, 1), 32 + 8 * k + blk);
+            for (u32 g = 0; g < 2; g++) put(at(0, 2 + g), 64 + 16 * k + 2 * blk + g);
+            for (u32 g = 0; g < 4; g++) put(at(0, 4 + g), 128 + 32 * k + 4 * blk + g);
+            for (u32 m = 0; m < 8; m++) put(at(1, m), 256 + 64 * k + 8 * blk + m);
+            for (u32 m = 0; m < 8; m++) put(at(2, m), 512 + 128 * k + 16 * blk + 2 * m + (q >> 1));
+          }
+        }
+      ok = cudaMalloc(&c->d_twx, tx.size() * 4) == cudaSuccess && cudaMemcpy(c->d_twx, tx.data(), tx.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+      c->v2.d_twx = c->d_twx;
+    }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     c->chunk = std::max<size_t>(1, bfhe_ctx::CHUNK / (4 * (size_t)sms)) * 4 * (size_t)sms; // whole waves of 4-gate CTAs
@@ -198,6 +227,7 @@ extern "C" void bfhe_destroy(bfhe_ctx *c) {
     cudaFree(c->d_tmp); cudaFree(c->d_ptr_in); cudaFree(c->d_ptr_out); cudaFree(c->e2e_slab);
     cudaFree(c->d_gates_b); cudaFree(c->d_ext_b);
     cudaFree(c->d_bk2); cudaFree(c->d_bk4); cudaFree(c->d_tw2); cudaFree(c->d_F);
+    cudaFree(c->d_bkx); cudaFree(c->d_twx);
     for (int i = 0; i < 2; i++) {
       if (c->ev_br[i]) cudaEventDestroy(c->ev_br[i]);
       if (c->ev_ks[i]) cudaEventDestroy(c->ev_ks[i]);
@@ -379,6 +409,14 @@ int bfhe::ensure_device_keys(bfhe_ctx *c) {
     BFHE_CUDA(cudaStreamSynchronize(c->stream));
     c->v2.d_bk2 = c->d_bk2;
     c->v2.d_bk4 = c->d_bk4;
+  }
+  cudaFree(c->d_bkx); c->d_bkx = nullptr; c->v2.d_bkx = nullptr;
+  if (c->d_twx && clx_supported(c->P, p.method == BFHE_AP)) { // key copy of the slot-sliced cluster kernel: [step][rank][polynomial][N/4]
+    BFHE_CUDA(cudaMalloc(&c->d_bkx, c->bk_words * 4));
+    int rc = launch_bk_slice_clx(c->d_bk, c->d_bkx, c->bk_words / N, c->stream);
+    if (rc) return cuda_fail((cudaError_t)rc, "bk_slice_clx");
+    BFHE_CUDA(cudaStreamSynchronize(c->stream));
+    c->v2.d_bkx = c->d_bkx;
   }
   { // KSK: [i][j(digit value)][k(digit index)][n+1]  ->  [i][k][j][rowlen]
     const u32 rowlen = c->ksk_elem_bytes == 2 ? 512 : p.ct_stride; // elements per padded row

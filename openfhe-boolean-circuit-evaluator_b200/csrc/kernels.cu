@@ -1171,6 +1171,7 @@ int blind_rotate_set_attrs() {
   rc |= br_attrs<9, 3, 9>();
   rc |= keyswitch_attrs();
   rc |= v2_set_attrs();
+  rc |= clx_set_attrs();
   return rc;
 }
 
@@ -1180,6 +1181,8 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   cudaStream_t st = (cudaStream_t)stream;
   const bool have_v2 = v2 && v2->d_bk2 && v2_supported(P, method_ap);
   if ((force_g == 16 || force_g == 32 || force_g == 64) && !have_v2) return (int)cudaErrorInvalidValue;
+  const bool have_clx = v2 && v2->d_bkx && v2->d_twx && v2->d_F && clx_supported(P, method_ap);
+  if (force_g == 128) return have_clx ? launch_blind_rotate_clx(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info) : (int)cudaErrorInvalidValue;
   if (force_g == 32) return launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   if (force_g == 64) return launch_blind_rotate_cl4(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   int dev = 0, sms = 148;

@@ -1,0 +1,499 @@
+// kernels_cl.cu -- GINX blind rotation of ONE gate on a 4-CTA thread-block cluster with ONE exchange per step ("slot-sliced" form).
+// STD128_OPT shape (N = 1024, dG = 4, Bg = 2^7).  Same arithmetic as blind_rotate_kernel in kernels.cu (the
+// reference reaches it through BinFHEContext::EvalBinGate, src/gate.cpp:133,172,200-202 in /root/reference).
+//
+// Round 1's cluster kernels split a step by ROWS for the transforms and by SLOTS for the external product, which costs two all-to-all
+// exchanges over DSMEM per step (digit rows out, product rows back); ncu showed them waiting on those exchanges 35 % of the time
+// (profiles/r1_blind_rotate_cluster4_ncu_summary.md).  This kernel slices everything by evaluation slot instead.  Write the transform of
+// size N as (two stages across the four blocks of N/4 coefficients) o (four independent sub-transforms of size N/4):
+//
+//   * every CTA keeps the WHOLE accumulator (both components, coefficient form, 8 coefficients per thread in registers);
+//   * CTA k computes, for all 8 digit polynomials, only block k of the two cross-block stages -- straight from the digits with three
+//     table look-ups per value (digit x {w1, w2, w1 w2} precomputed for the 128 digit values), no multiplication -- and then its own
+//     256-point sub-transform of each (one warp per digit polynomial, 8 values per lane: 3 + 3 register stages, one shared-memory
+//     transpose, 2 stages across lanes by shuffle);
+//   * it multiplies ITS 256 slots of the 8 rows with ITS quarter of the step's key tile (32 KB, TMA bulk copy, double buffered), and
+//     runs the 256-point inverse sub-transform of the two product components (one warp each);
+//   * the only exchange: the 2 x 256 partial values go to the three peers (st.async, counted on the receiver's mbarrier, 6 KB in and
+//     out per CTA and step); every CTA then finishes the inverse transform redundantly (two cross-block stages, 8 multiplications per
+//     thread), adds to its copy of the accumulator and cuts the next digits.
+//
+// No cluster-scope fence or barrier.cluster inside the step loop; receive buffers and their mbarriers alternate by step parity, so a
+// CTA that runs one step ahead cannot overwrite or miscount data its peer is still reading.
+#include "common.hpp"
+#include <cuda_runtime.h>
+
+namespace bfhe {
+namespace clx {
+
+constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, NPAD = 512, R = 4, NB = N / R, THREADS = 256;
+constexpr int KEYPOLYS = 2 * ROWS * 2;
+constexpr u32 DIGIT_OFF = 64u + (64u << 7) + (64u << 14) + (64u << 21);
+constexpr u32 SOLINAS_Q = (1u << 27) - (1u << 11) + 1;
+constexpr u32 KEYBYTES = (u32)KEYPOLYS * NB * 4;   // 32 KB per CTA and step
+constexpr u32 RECV_TX = (u32)(R - 1) * 2 * NB * 4; // bytes the three peers push into a CTA per step
+
+// per-rank twiddle block (host-generated, engine.cu clx_tables): fw | fws | iw | iws, each TWW words:
+//   [0, 8)                 pass A (register stages across the 32-strided values), uniform over the warp: w[1], w[2..3], w[4..7]
+//   [8 + 256 s, + 256)     s = 0: pass B register stages, s = 1 / 2: the two shuffle stages; each [chunk 2][lane 32][4] (8 per lane)
+constexpr int TWW = 8 + 3 * 256;
+
+__device__ __forceinline__ u32 redc(u64 s, u32 Q, u32 qinv_neg) { // s * 2^-32 mod Q, lazy
+  const u32 m = (u32)s * qinv_neg;
+  return (u32)((s + (u64)m * Q) >> 32);
+}
+__device__ __forceinline__ u32 lazy_reduce(u32 x, u32 Q) { return x - (x >> 27) * Q; } // floor(2^32 / Q) = 32: any x -> [0, 2Q)
+__device__ __forceinline__ u32 csub(u32 x, u32 Q) { return min(x, x - Q); }
+__device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q) { return x * w - __umulhi(x, ws) * Q; } // [0, 2Q)
+__host__ __device__ __forceinline__ u32 f_index(u32 k) { return ((k >> 5) & 63u) | ((k & 31u) << 6); } // table of psi^k - 1, see kernels_v2.cu
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(
+                   smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ u32 cluster_rank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ u32 dsmem_addr(const void *local, u32 rank) { // shared::cluster address of `local` in CTA `rank`
+  u32 a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(local)), "r"(rank));
+  return a;
+}
+// remote store whose arrival is counted on the destination CTA's mbarrier (complete_tx): the receiver needs no cluster-scope fence
+__device__ __forceinline__ void st_async4(u32 dsmem, uint4 v, u32 dsmem_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dsmem), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "r"(dsmem_bar)
+               : "memory");
+}
+
+// ---- 8-value register stages.  Stage with half-size T pairs a = g * 2T + (i % T), b = a + T and uses twiddle w[8 / (2T) + g] ----
+template <int T> __device__ __forceinline__ void ct8_stage(u32 (&x)[8], const u32 (&w)[8], const u32 (&ws)[8], u32 Q, u32 Q2) {
+  u32 t[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int g = i / T, b = g * 2 * T + (i % T) + T, p = 4 / T + g;
+    t[i] = mul_shoup(x[b], w[p], ws[p], Q);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int g = i / T, a = g * 2 * T + (i % T), b = a + T;
+    x[b] = x[a] - t[i] + Q2; // no range correction: values grow by 2Q per stage and stay below 2^32 (21Q after all ten stages)
+    x[a] = x[a] + t[i];
+  }
+}
+// Gentleman-Sande stage; B = bound of the inputs in units of Q.  Sums are pulled back below 2Q when they would pass 32Q at the next stage.
+template <int T, int B> struct Gs8 {
+  static constexpr bool RED = (2 * B > 16);
+  static constexpr int OUTB = RED ? 2 : 2 * B;
+  __device__ __forceinline__ static void run(u32 (&x)[8], const u32 (&w)[8], const u32 (&ws)[8], u32 Q) {
+    static_assert(B <= 16, "GS input bound too large");
+    u32 D[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int g = i / T, a = g * 2 * T + (i % T), b = a + T;
+      D[i] = x[a] - x[b] + B * Q;
+      const u32 S = x[a] + x[b];
+      x[a] = RED ? lazy_reduce(S, Q) : S;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int g = i / T, b = g * 2 * T + (i % T) + T, p = 4 / T + g;
+      x[b] = mul_shoup(D[i], w[p], ws[p], Q);
+    }
+  }
+};
+template <int B> struct GsShfl { // one stage across lanes `mask` apart; the upper lane holds b
+  static constexpr bool RED = (2 * B > 16);
+  static constexpr int OUTB = RED ? 2 : 2 * B;
+  __device__ __forceinline__ static void run(u32 (&x)[8], const u32 (&w)[8], const u32 (&ws)[8], u32 Q, int mask, bool upper) {
+    static_assert(B <= 16, "GS input bound too large");
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+      const u32 o = __shfl_xor_sync(0xffffffffu, x[m], mask);
+      const u32 D = o - x[m] + B * Q; // upper lane: (lower - upper) * w
+      const u32 pr = mul_shoup(D, w[m], ws[m], Q);
+      const u32 S = x[m] + o;
+      x[m] = upper ? pr : (RED ? lazy_reduce(S, Q) : S);
+    }
+  }
+};
+__device__ __forceinline__ void ct_shfl(u32 (&x)[8], const u32 (&w)[8], const u32 (&ws)[8], u32 Q, u32 Q2, int mask, bool upper) {
+#pragma unroll
+  for (int m = 0; m < 8; m++) {
+    const u32 v = upper ? mul_shoup(x[m], w[m], ws[m], Q) : x[m];
+    const u32 o = __shfl_xor_sync(0xffffffffu, v, mask);
+    x[m] = upper ? (o - v + Q2) : (v + o);
+  }
+}
+__device__ __forceinline__ void load8(const u32 *tab, u32 (&w)[8], int lane) { // [chunk 2][lane 32][4]
+  const uint4 a = reinterpret_cast<const uint4 *>(tab)[lane], b = reinterpret_cast<const uint4 *>(tab)[32 + lane];
+  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+// word offset of position i (0..255) of a sub-transform row: 32-word groups rotated by 4 * group, so that both the 32-strided access of
+// pass A (i = lane + 32 m) and the 4-strided access of pass B (i = 32 blk + q + 4 m', lane = 4 blk + q) are bank-conflict free
+__device__ __forceinline__ int rowpos(int i) { return (i & ~31) | ((i + 4 * (i >> 5)) & 31); }
+
+// in-place position (0 .. N-1, Cooley-Tukey order: slot P holds the evaluation at psi^(2 bitrev(P) + 1)) of MAC slot t of CTA k
+__host__ __device__ __forceinline__ int slot_position(int k, int t) {
+  const int lane = t >> 3, m = t & 7, blk = lane >> 2, q = lane & 3;
+  return NB * k + 32 * blk + q + 4 * m;
+}
+
+struct Smem { // word offsets
+  static constexpr int rbuf = 0;                              // [parity 2][source CTA R][component 2][NB]
+  static constexpr int dct = rbuf + 2 * R * 2 * NB;           // [ROWS][NB]
+  static constexpr int prod = dct + ROWS * NB;                // [2][NB]
+  static constexpr int key = prod + 2 * NB;                   // [parity 2][KEYPOLYS][NB]
+  static constexpr int tw = key + 2 * KEYPOLYS * NB;          // fw | fws | iw | iws, TWW words each (padded to a multiple of 4)
+  static constexpr int lut = tw + 4 * ((TWW + 3) & ~3);       // [3][128][32]
+  static constexpr int F = lut + 3 * 128 * 32;                // [2N]
+  static constexpr int idx = F + 2 * N;                       // u16 [NPAD]
+  static constexpr int bars = idx + NPAD / 2;                 // kbar[2], rbar[2]
+  static constexpr int words = bars + 8;
+  static constexpr size_t bytes = (size_t)words * 4;
+};
+
+__global__ void __cluster_dims__(R, 1, 1) __launch_bounds__(THREADS, 1)
+blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count, const u32 *__restrict__ bkx,
+                        const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  u32 *sm = reinterpret_cast<u32 *>(smem_raw);
+  u32 *rbuf = sm + Smem::rbuf, *dct = sm + Smem::dct, *prod = sm + Smem::prod, *s_key = sm + Smem::key, *s_tw = sm + Smem::tw;
+  u32 *s_lut = sm + Smem::lut, *s_F = sm + Smem::F;
+  u16 *s_idx = reinterpret_cast<u16 *>(sm + Smem::idx);
+  u64 *kbar = reinterpret_cast<u64 *>(sm + Smem::bars), *rbar = kbar + 2;
+  __shared__ u32 s_b;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 k = cluster_rank();
+  const size_t gi = blockIdx.x / R;
+  const u32 Q = P.Q, Q2 = P.Q2, q = P.q, n = P.n, qinv = P.qinv_neg;
+  const DevGate dg = gates[gi];
+  constexpr int TWP = (TWW + 3) & ~3;
+
+  if (tid == 0) {
+    mbar_init(kbar + 0, 1); mbar_init(kbar + 1, 1); mbar_init(rbar + 0, 1); mbar_init(rbar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 4 * TWP; i += THREADS) s_tw[i] = g_tw[(size_t)k * 4 * TWP + i];
+  for (int i = tid; i < 2 * N; i += THREADS) s_F[i] = g_F[i];
+  { // look-up tables of the two cross-block forward stages for block k: y_k = d0 + c1 d2 + c2 d1 + c3 d3 with
+    //   k = 0: (+w1, +w2, +w2 w1)   k = 1: (+w1, -w2, -w2 w1)   k = 2: (-w1, +w3, -w3 w1)   k = 3: (-w1, -w3, +w3 w1)
+    // (w1 = psi^bitrev(1), w2 = psi^bitrev(2), w3 = psi^bitrev(3): the twiddles of the stages with 1 and 2 groups), entries
+    // c * (digit - B/2) mod Q for the 128 digit values, one copy per bank
+    const u64 w1 = P.tw[1], wb = (k & 2) ? P.tw[3] : P.tw[2];
+    const u64 c1 = (k & 2) ? Q - w1 : w1;
+    const u64 c2 = (k & 1) ? Q - wb : wb;
+    u64 c3 = wb * w1 % Q;
+    if (k == 1 || k == 2) c3 = Q - c3;
+    for (int e = tid; e < 3 * 128; e += THREADS) {
+      const int tab = e >> 7, d = e & 127;
+      const u64 c = tab == 0 ? c1 : tab == 1 ? c2 : c3;
+      const u32 v = (u32)(c * (u64)((d + Q - 64) % Q) % Q);
+#pragma unroll 4
+      for (int l = 0; l < 32; l++) s_lut[e * 32 + l] = v;
+    }
+  }
+  { // LWE prep, as in the other kernels (every CTA of the cluster computes it)
+    const u32 gate = dg.op & 0xff;
+    for (u32 i = tid; i <= n; i += THREADS) {
+      u32 x = dg.in0[i];
+      if (dg.op & OP_NEG0) x = (i == n) ? (q / 4 + q - x) % q : (q - x) % q;
+      u32 v;
+      if (gate == OP_BOOTSTRAP) v = (i == n) ? (x + q / 4) % q : x;
+      else {
+        u32 y = dg.in1[i];
+        if (dg.op & OP_NEG1) y = (i == n) ? (q / 4 + q - y) % q : (q - y) % q;
+        v = (gate == OP_XOR_FAST || gate == OP_XNOR_FAST) ? (2 * (x + q - y)) % q : (x + y) % q;
+      }
+      if (i == n) s_b = v;
+      else s_idx[i] = (u16)(((q - v) % q) * P.factor);
+    }
+  }
+  __syncthreads();
+
+  auto issue_keys = [&](u32 step) { // thread 0: this CTA's 32 KB of step `step`: [step][rank][polynomial][NB] contiguous
+    u64 *bar = kbar + (step & 1);
+    mbar_expect_tx(bar, KEYBYTES);
+    const u32 *src = bkx + ((size_t)step * R + k) * KEYPOLYS * NB;
+    u32 *dst = s_key + (size_t)(step & 1) * KEYPOLYS * NB;
+    bulk_g2s(dst, src, 16384, bar);
+    bulk_g2s(dst + 4096, src + 4096, 16384, bar);
+  };
+  static_assert(KEYBYTES == 2 * 16384, "two bulk copies");
+  if (tid == 0 && n > 0) {
+    issue_keys(0);
+    if (n > 1) issue_keys(1);
+  }
+
+  // accumulator: thread t holds coefficients t + 256 i1 (i1 = 0..3) of both components, canonical [0, Q)
+  u32 acc[2][4];
+  {
+    const u32 gate = dg.op & 0xff;
+    const u32 q1 = P.gate_const[gate == OP_BOOTSTRAP ? OP_AND : gate], q2 = (q1 + q / 2) % q, b = s_b;
+#pragma unroll
+    for (int i1 = 0; i1 < 4; i1++) {
+      acc[0][i1] = 0;
+      const u32 idx = tid + NB * i1;
+      u32 v = 0;
+      if (idx % P.factor == 0) {
+        const u32 t = (b + q - idx / P.factor) % q;
+        const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
+        v = in ? Q - P.Q8 : P.Q8;
+      }
+      acc[1][i1] = v;
+    }
+  }
+  cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
+
+  // per-thread constants
+  const u32 ex = 2 * (__brev((u32)slot_position((int)k, tid)) >> (32 - LOGN)) + 1; // MAC slot tid evaluates at psi^ex
+  const u32 *fw = s_tw, *fws = s_tw + TWP, *iw = s_tw + 2 * TWP, *iws = s_tw + 3 * TWP;
+  const u32 iw1 = P.itw[1], iw1s = P.itws[1], iwb = P.itw[2], iwbs = P.itws[2], iwc = P.itw[3], iwcs = P.itws[3];
+  const int blk = lane >> 2, qq = lane & 3;
+  u32 peer_rbuf[R - 1], peer_bar[R - 1]; // shared::cluster addresses in the three peers (receive buffer, rbar[0]; rbar[1] is 8 bytes on)
+#pragma unroll
+  for (int p = 0; p < R - 1; p++) {
+    const u32 dest = (k + 1 + p) % R;
+    peer_rbuf[p] = dsmem_addr(rbuf, dest);
+    peer_bar[p] = dsmem_addr(rbar, dest);
+  }
+
+  for (u32 step = 0; step < n; step++) {
+    const u32 par = step & 1;
+    if (tid == 0) mbar_expect_tx(rbar + par, RECV_TX); // this step's receive expectation (early pushes merely run the count negative)
+    // ---- phase A: digits of the accumulator -> block k of the two cross-block forward stages, by table look-up ----
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      u32 dp[4];
+#pragma unroll
+      for (int i1 = 0; i1 < 4; i1++) dp[i1] = ((acc[c][i1] < (Q >> 1)) ? acc[c][i1] : acc[c][i1] - Q) + DIGIT_OFF; // centred + offset
+#pragma unroll
+      for (int l = 0; l < DG; l++) {
+        const u32 d0 = (dp[0] >> (LOGBG * l)) & 127u, d1 = (dp[1] >> (LOGBG * l)) & 127u, d2 = (dp[2] >> (LOGBG * l)) & 127u,
+                  d3 = (dp[3] >> (LOGBG * l)) & 127u;
+        const u32 y = (d0 + (Q - 64u)) + s_lut[((0 * 128 + d2) << 5) + lane] + s_lut[((1 * 128 + d1) << 5) + lane] + s_lut[((2 * 128 + d3) << 5) + lane];
+        dct[(c + 2 * l) * NB + rowpos(tid)] = y; // lazy, < 4Q + 64
+      }
+    }
+    __syncthreads();
+    // ---- phase B: warp w transforms row w (256 points, 8 per lane) ----
+    {
+      u32 *row = dct + warp * NB;
+      u32 x[8], w[8], ws[8];
+#pragma unroll
+      for (int m = 0; m < 8; m++) x[m] = row[rowpos(lane + 32 * m)];
+#pragma unroll
+      for (int p = 1; p < 8; p++) { w[p] = fw[p]; ws[p] = fws[p]; } // uniform over the warp
+      ct8_stage<4>(x, w, ws, Q, Q2); ct8_stage<2>(x, w, ws, Q, Q2); ct8_stage<1>(x, w, ws, Q, Q2);
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 8; m++) row[rowpos(lane + 32 * m)] = x[m];
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 8; m++) x[m] = row[rowpos(32 * blk + qq + 4 * m)];
+      load8(fw + 8, w, lane); load8(fws + 8, ws, lane);
+      ct8_stage<4>(x, w, ws, Q, Q2); ct8_stage<2>(x, w, ws, Q, Q2); ct8_stage<1>(x, w, ws, Q, Q2);
+      load8(fw + 8 + 256, w, lane); load8(fws + 8 + 256, ws, lane);
+      ct_shfl(x, w, ws, Q, Q2, 2, (qq & 2) != 0);
+      load8(fw + 8 + 512, w, lane); load8(fws + 8 + 512, ws, lane);
+      ct_shfl(x, w, ws, Q, Q2, 1, (qq & 1) != 0);
+      __syncwarp();
+      *reinterpret_cast<uint4 *>(row + 8 * lane) = make_uint4(x[0], x[1], x[2], x[3]); // MAC slot 8 lane + m
+      *reinterpret_cast<uint4 *>(row + 8 * lane + 4) = make_uint4(x[4], x[5], x[6], x[7]);
+    }
+    __syncthreads();
+    if (tid == 0 && step >= 1 && step + 1 < n) { // the key buffer of parity (step + 1) & 1 was last read by the product of step - 1
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue_keys(step + 1);
+    }
+    // ---- phase C: external product on my 256 slots, one slot per thread ----
+    mbar_wait(kbar + par, (step >> 1) & 1);
+    {
+      const u32 *kt = s_key + (size_t)par * KEYPOLYS * NB + tid;
+      const u32 m = s_idx[step];
+      const u32 y = m * ex, ny = 0u - y;
+      const u32 fp = s_F[f_index(y)], fn = s_F[f_index(ny)]; // (X^m - 1), (X^-m - 1) at this slot, Montgomery form
+      u64 sp[2] = {0, 0}, sn[2] = {0, 0};
+#pragma unroll
+      for (int rw = 0; rw < ROWS; rw++) {
+        const u32 d = dct[rw * NB + tid];
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          sp[cc] += (u64)d * kt[((0 * ROWS + rw) * 2 + cc) * NB];
+          sn[cc] += (u64)d * kt[((1 * ROWS + rw) * 2 + cc) * NB];
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++)
+        prod[cc * NB + tid] = redc((u64)redc(sp[cc], Q, qinv) * fp + (u64)redc(sn[cc], Q, qinv) * fn, Q, qinv); // < 2Q
+    }
+    __syncthreads();
+    // ---- phase D: warps 0 / 1: inverse sub-transform of product component 0 / 1, push the partial values to the peers ----
+    if (warp < 2) {
+      u32 x[8], w[8], ws[8];
+      const u32 *pr = prod + warp * NB;
+      {
+        const uint4 a = *reinterpret_cast<const uint4 *>(pr + 8 * lane), b = *reinterpret_cast<const uint4 *>(pr + 8 * lane + 4);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      }
+      load8(iw + 8 + 512, w, lane); load8(iws + 8 + 512, ws, lane);
+      using S7 = GsShfl<2>;
+      S7::run(x, w, ws, Q, 1, (qq & 1) != 0);
+      load8(iw + 8 + 256, w, lane); load8(iws + 8 + 256, ws, lane);
+      using S6 = GsShfl<S7::OUTB>;
+      S6::run(x, w, ws, Q, 2, (qq & 2) != 0);
+      load8(iw + 8, w, lane); load8(iws + 8, ws, lane);
+      using S5 = Gs8<1, S6::OUTB>; using S4 = Gs8<2, S5::OUTB>; using S3 = Gs8<4, S4::OUTB>;
+      S5::run(x, w, ws, Q); S4::run(x, w, ws, Q); S3::run(x, w, ws, Q);
+      u32 *row = dct + warp * NB; // scratch for the transpose (rows 0 / 1 are dead after the product)
+#pragma unroll
+      for (int m = 0; m < 8; m++) row[rowpos(32 * blk + qq + 4 * m)] = x[m];
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 8; m++) x[m] = row[rowpos(lane + 32 * m)];
+#pragma unroll
+      for (int p = 1; p < 8; p++) { w[p] = iw[p]; ws[p] = iws[p]; }
+      using S2 = Gs8<1, S3::OUTB>; using S1 = Gs8<2, S2::OUTB>; using S0 = Gs8<4, S1::OUTB>;
+      S2::run(x, w, ws, Q); S1::run(x, w, ws, Q); S0::run(x, w, ws, Q);
+      static_assert(S0::OUTB <= 4, "partial values must stay below 4Q for the cross-block stages");
+      // my own copy, natural order j = lane + 32 m; then 16-byte pushes of 4 consecutive j to the three peers
+      u32 *mine = rbuf + ((par * R + k) * 2 + warp) * NB;
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 8; m++) mine[lane + 32 * m] = x[m];
+      __syncwarp();
+      const uint4 v0 = *reinterpret_cast<const uint4 *>(mine + 4 * lane), v1 = *reinterpret_cast<const uint4 *>(mine + 128 + 4 * lane);
+      const u32 off = (u32)(((par * R + k) * 2 + warp) * NB + 4 * lane) * 4u;
+#pragma unroll
+      for (int p = 0; p < R - 1; p++) {
+        st_async4(peer_rbuf[p] + off, v0, peer_bar[p] + 8u * par);
+        st_async4(peer_rbuf[p] + off + 512u, v1, peer_bar[p] + 8u * par);
+      }
+    }
+    __syncthreads(); // my own partial values are visible to all my warps
+    mbar_wait(rbar + par, (step >> 1) & 1); // ... and the peers' have landed
+    // ---- phase E: the two cross-block inverse stages for coefficients tid + 256 i1, both components; accumulate ----
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const u32 *rb = rbuf + (size_t)(par * R) * 2 * NB + c * NB + tid;
+      const u32 p0 = rb[0 * 2 * NB], p1 = rb[1 * 2 * NB], p2 = rb[2 * 2 * NB], p3 = rb[3 * 2 * NB]; // partial values of blocks 0..3, < 4Q
+      const u32 u0 = p0 + p1, u1 = mul_shoup(p0 - p1 + 4 * Q, iwb, iwbs, Q);
+      const u32 u2 = p2 + p3, u3 = mul_shoup(p2 - p3 + 4 * Q, iwc, iwcs, Q);
+      const u32 x0 = u0 + u2, x2 = mul_shoup(u0 - u2 + 8 * Q, iw1, iw1s, Q); // u0, u2 < 8Q
+      const u32 x1 = u1 + u3, x3 = mul_shoup(u1 - u3 + 2 * Q, iw1, iw1s, Q); // u1, u3 < 2Q
+      acc[c][0] = csub(acc[c][0] + csub(lazy_reduce(x0, Q), Q), Q);
+      acc[c][1] = csub(acc[c][1] + csub(lazy_reduce(x1, Q), Q), Q);
+      acc[c][2] = csub(acc[c][2] + csub(x2, Q), Q);
+      acc[c][3] = csub(acc[c][3] + csub(x3, Q), Q);
+    }
+  }
+
+  // ---- epilogue: sample extraction (a14) and ModSwitch Q -> qKS (a15); CTA k writes the coefficients tid + 256 k ----
+  {
+    u32 *e = ext + gi * (N + 4);
+    const u64 qKS = P.qKS;
+    auto modswitch = [&](u32 v) -> u32 { return (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS); };
+#pragma unroll
+    for (int i1 = 0; i1 < 4; i1++) {
+      if ((u32)i1 != k) continue;
+      const u32 j = tid + NB * i1;
+      if (acc_dbg) { acc_dbg[(gi * 2 + 0) * N + j] = acc[0][i1]; acc_dbg[(gi * 2 + 1) * N + j] = acc[1][i1]; }
+      const u32 a = acc[0][i1];
+      const u32 v = (j == 0) ? a : (a == 0 ? 0 : Q - a); // Transpose: a'_0 = a_0, a'_k = -a_{N-k}
+      e[(j == 0) ? 0 : N - j] = modswitch(v);
+      if (j == 0) e[N] = modswitch(csub(acc[1][i1] + P.Q8, Q));
+    }
+  }
+  cluster_sync_all(); // a CTA must not exit while its peers may still push into its shared memory
+}
+
+// key copy of this kernel: [step][rank][polynomial][slot t] <- evaluation-form key of kernels.cu ([chunk][lane][4] word order, slot P =
+// 32 lane + 4 chunk + r holds the evaluation at psi^(2 bitrev(P) + 1))
+__global__ void bk_slice_clx_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t nsteps) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsteps * KEYPOLYS * N; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t step = i / ((size_t)KEYPOLYS * N), rem = i % ((size_t)KEYPOLYS * N);
+    const int rk = (int)(rem / ((size_t)KEYPOLYS * NB)), pl = (int)((rem / NB) % KEYPOLYS), t = (int)(rem % NB);
+    const int Ppos = slot_position(rk, t), sl = Ppos >> 5, j = Ppos & 31;
+    dst[i] = src[(step * KEYPOLYS + pl) * N + ((j >> 2) * 32 + sl) * 4 + (j & 3)];
+  }
+}
+
+} // namespace clx
+
+bool clx_supported(const DevConst &P, int method_ap) {
+  return !method_ap && P.N == 1024 && P.dG == 4 && P.logBG == 7 && P.Q == clx::SOLINAS_Q && P.n <= (u32)clx::NPAD;
+}
+size_t clx_tw_words() { return (size_t)clx::R * 4 * ((clx::TWW + 3) & ~3); }
+static int clx_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < 64 ? dev : 0;
+}
+int clx_set_attrs() {
+  return (int)cudaFuncSetAttribute(clx::blind_rotate_clx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clx::Smem::bytes);
+}
+static int clx_attrs_once() { // per device, and never under stream capture: at first use
+  static bool done[64];
+  const int d = clx_device_slot();
+  if (done[d]) return 0;
+  const int rc = clx_set_attrs();
+  if (rc == 0) done[d] = true;
+  return rc;
+}
+int clx_max_gates() { // 4-CTA clusters of this kernel the device keeps co-resident, one CTA per SM
+  static int cached[64];
+  static bool have[64];
+  const int d = clx_device_slot();
+  if (!have[d]) {
+    int nmax = 0;
+    if (clx_attrs_once() == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(clx::R * 148, 1, 1);
+      cfg.blockDim = dim3(clx::THREADS, 1, 1);
+      cfg.dynamicSmemBytes = clx::Smem::bytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = clx::R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&nmax, clx::blind_rotate_clx_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nmax = 0; }
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (nmax > sms / clx::R) nmax = sms / clx::R;
+    }
+    cached[d] = nmax;
+    have[d] = true;
+  }
+  return cached[d];
+}
+int launch_bk_slice_clx(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
+  if (npoly == 0) return 0;
+  clx::bk_slice_clx_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly / clx::KEYPOLYS);
+  return (int)cudaGetLastError();
+}
+int launch_blind_rotate_clx(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
+                            LaunchInfo *info) {
+  if (count <= 0) return 0;
+  if (int rc = clx_attrs_once()) return rc;
+  if (info) { info->gates_per_cta = 1; info->ctas = clx::R * count; info->smem_bytes = clx::Smem::bytes; }
+  clx::blind_rotate_clx_kernel<<<clx::R * count, clx::THREADS, clx::Smem::bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bkx, vb.d_twx, vb.d_F,
+                                                                                                   d_ext, d_acc_dbg);
+  return (int)cudaGetLastError();
+}
+
+} // namespace bfhe
