@@ -242,7 +242,7 @@ def test_kernel_forms_agree_on_every_wire(bfhe):
     v = VECTORS["mult_32x32"]["vectors"][0]
     ref = None
     try:
-        for form in (8, 0, 32, 64, 32, 64, 16, 4, 0):
+        for form in (8, 0, 32, 64, 128, 32, 128, 64, 128, 16, 4, 0):
             ctx.dbg_set_gates_per_cta(form)
             assert _run_encrypted(c, v, seed=11, verify=False) == v["golden"], form
             slab = c.download_slab()

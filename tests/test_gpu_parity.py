@@ -50,7 +50,7 @@ def _random_gates(bfhe, rng, n_in, count, ops):
 
 
 @pytest.mark.parametrize("ps_name,m_name", CONFIGS)
-@pytest.mark.parametrize("gpc", [4, 8, 16, 32, 64])  # 16 = kernels_v2.cu, 32 / 64 = one gate on a 2- / 4-CTA cluster (STD128_OPT GINX only)
+@pytest.mark.parametrize("gpc", [4, 8, 16, 32, 64, 128])  # 16 = kernels_v2.cu, 32 / 64 = one gate on a 2- / 4-CTA cluster, 128 = slot-sliced 4-CTA cluster (STD128_OPT GINX only)
 def test_blind_rotate_accumulator(bfhe, orc, ps_name, m_name, gpc):
     """a9-a12: accumulator after the whole blind rotation, coefficient form, vs the oracle's evaluation-form loop."""
     if gpc >= 16 and (ps_name, m_name) != ("STD128_OPT", "GINX"):
@@ -76,7 +76,7 @@ def test_blind_rotate_accumulator(bfhe, orc, ps_name, m_name, gpc):
 
 
 @pytest.mark.parametrize("ps_name,m_name", CONFIGS + [("STD128_OPT", "AP")])
-@pytest.mark.parametrize("gpc", [1, 2, 4, 8, 16, 32, 64])  # 8 = latency variant (one gate per CTA, TMA-staged key); 16 = kernels_v2.cu; 32 / 64 = clusters
+@pytest.mark.parametrize("gpc", [1, 2, 4, 8, 16, 32, 64, 128])  # 8 = latency variant (one gate per CTA, TMA-staged key); 16 = kernels_v2.cu; 32 / 64 / 128 = clusters
 def test_bingate_bit_exact(bfhe, orc, ps_name, m_name, gpc):
     """a7: output LWE ciphertexts of a wavefront are bit-identical to the oracle for every gate type (the 12-op list: all eight
     BINGATE values, Bootstrap, and fused EvalNOT operands), on every kernel form, STD128_OPT AP included (a11)."""
