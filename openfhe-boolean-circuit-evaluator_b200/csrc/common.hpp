@@ -27,6 +27,8 @@ struct DevConst {
   u32 ninv, ninvs; // N^-1 mod Q and its Shoup companion (debug kernels only)
   u32 nM, nMs;     // N^-1 * 2^32 mod Q (+Shoup): coefficient-form key -> device form
   u32 gate_const[9];
+  u32 sol_zero;           // 0, opaque to the compiler (3-input adds stay on the ALU pipe)
+  u32 sol_sh16, sol_sh11; // 16 and 11 for Q = 2^27 - 2^11 + 1: shift amounts of the ALU-pipe form of t*Q (kernels.cu mul_shoup<true>)
   // psi^bitrev(k), k in [1,32): the twiddles of every NTT stage whose butterflies span >= 32 indices.
   u32 tw[32], tws[32], itw[32], itws[32];
 };

@@ -98,6 +98,7 @@ extern "C" bfhe_ctx *bfhe_create(int paramset, int method, int device) {
   P.mu = (u32)((1ull << 32) / Q);
   P.oneM = (u32)((1ull << 32) % Q);
   P.Q8 = (u32)(Q / 8 + 1);
+  P.sol_sh16 = 16; P.sol_sh11 = 11; P.sol_zero = 0;
   P.n = p.n; P.N = N; P.q = p.q; P.factor = 2 * N / p.q;
   P.qKS = (u32)p.qKS; P.baseKS = p.baseKS; P.dKS = p.dKS;
   P.baseR = p.baseR; P.dR = p.dR; P.dG = p.dG; P.logBG = ilog2_ceil(p.baseG);
@@ -175,32 +176,32 @@ extern "C" bfhe_ctx *bfhe_create(int paramset, int method, int device) {
            cudaMemcpy(c->d_F, F.data(), F.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
       c->v2.d_tw2 = c->d_tw2; c->v2.d_F = c->d_F;
     }
-    if (ok && clx_supported(P, method == BFHE_AP)) { // per-rank twiddle blocks of the slot-sliced cluster kernel (layout: kernels_cl.cu TWW)
+    if (ok && clx_supported(P, method == BFHE_AP)) { // per-rank twiddle blocks of the slot-sliced cluster kernel (layout: kernels_cl.cu TWF / TWI)
       // CTA k runs the sub-transform of block k (in-place positions 256 k + i, i < 256) as: pass A (lane holds i = lane + 32 m),
-      // pass B (lane = 4 blk + q holds i = 32 blk + q + 4 m), two stages across lanes.  A stage with G groups uses tw[G + group],
-      // group = position / (N / G) -- the table order of HostNtt (tw[k] = psi^bitrev(k)).
-      const size_t TWW = 8 + 3 * 256, TWP = (TWW + 3) & ~(size_t)3;
+      // pass B (lane = 4 blk + q holds i = 32 blk + q + 4 m), pass C (lane holds i = 8 lane + j).  A stage with G groups uses tw[G + group],
+      // group = position / (N / G) -- the table order of HostNtt (tw[k] = psi^bitrev(k)).  The inverse runs the five narrowest stages
+      // as shuffles in the external-product threads (slot t = position t) and the three widest in pass-A layout.
+      const size_t TWF = 8 + 2 * 256, TWI = 8 + 5 * 256, TWR = 2 * TWF + 2 * TWI;
       std::vector<u32> tx(clx_tw_words(), 0);
-      for (u32 k = 0; k < 4; k++)
-        for (int inv = 0; inv < 2; inv++) {
-          u32 *w = tx.data() + ((size_t)k * 4 + 2 * inv) * TWP, *ws = w + TWP;
-          auto put = [&](size_t off, u32 idx) {
-            const u32 v = inv ? c->hntt.itw[idx] : c->hntt.tw[idx];
-            w[off] = v; ws[off] = shoup32(v, Q);
-          };
-          put(1, 4 + k);
-          for (u32 g = 0; g < 2; g++) put(2 + g, 8 + 2 * k + g);
-          for (u32 g = 0; g < 4; g++) put(4 + g, 16 + 4 * k + g);
-          for (u32 lane = 0; lane < 32; lane++) {
-            const u32 blk = lane >> 2, q = lane & 3;
-            auto at = [&](int s, u32 e) { return 8 + 256 * (size_t)s + ((size_t)(e >> 2) * 32 + lane) * 4 + (e & 3); }; // [chunk][lane][4]
-            put(at(0, 1), 32 + 8 * k + blk);
-            for (u32 g = 0; g < 2; g++) put(at(0, 2 + g), 64 + 16 * k + 2 * blk + g);
-            for (u32 g = 0; g < 4; g++) put(at(0, 4 + g), 128 + 32 * k + 4 * blk + g);
-            for (u32 m = 0; m < 8; m++) put(at(1, m), 256 + 64 * k + 8 * blk + m);
-            for (u32 m = 0; m < 8; m++) put(at(2, m), 512 + 128 * k + 16 * blk + 2 * m + (q >> 1));
-          }
+      for (u32 k = 0; k < 4; k++) {
+        u32 *fw = tx.data() + (size_t)k * TWR, *fws = fw + TWF, *iw = fw + 2 * TWF, *iws = iw + TWI;
+        auto putf = [&](size_t off, u32 idx) { fw[off] = c->hntt.tw[idx]; fws[off] = shoup32(c->hntt.tw[idx], Q); };
+        auto puti = [&](size_t off, u32 idx) { iw[off] = c->hntt.itw[idx]; iws[off] = shoup32(c->hntt.itw[idx], Q); };
+        putf(1, 4 + k); puti(1, 4 + k);
+        for (u32 g = 0; g < 2; g++) { putf(2 + g, 8 + 2 * k + g); puti(2 + g, 8 + 2 * k + g); }
+        for (u32 g = 0; g < 4; g++) { putf(4 + g, 16 + 4 * k + g); puti(4 + g, 16 + 4 * k + g); }
+        for (u32 lane = 0; lane < 32; lane++) {
+          const u32 blk = lane >> 2;
+          auto at = [&](int s, u32 e) { return 8 + 256 * (size_t)s + ((size_t)(e >> 2) * 32 + lane) * 4 + (e & 3); }; // [chunk][lane][4]
+          putf(at(0, 1), 32 + 8 * k + blk);
+          for (u32 g = 0; g < 2; g++) putf(at(0, 2 + g), 64 + 16 * k + 2 * blk + g);
+          for (u32 g = 0; g < 4; g++) putf(at(0, 4 + g), 128 + 32 * k + 4 * blk + g);
+          for (u32 g = 0; g < 2; g++) putf(at(1, 2 + g), 256 + 64 * k + 2 * lane + g);
+          for (u32 g = 0; g < 4; g++) putf(at(1, 4 + g), 512 + 128 * k + 4 * lane + g);
         }
+        for (u32 s5 = 0; s5 < 5; s5++)
+          for (u32 t = 0; t < 256; t++) puti(8 + 256 * (size_t)s5 + t, (512u >> s5) + ((256 * k + t) >> (s5 + 1)));
+      }
       ok = cudaMalloc(&c->d_twx, tx.size() * 4) == cudaSuccess && cudaMemcpy(c->d_twx, tx.data(), tx.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
       c->v2.d_twx = c->d_twx;
     }

@@ -52,12 +52,45 @@ bool kernels_built_for_solinas_q() { return BFHE_SOLINAS_Q != 0; }
 // SOL selects where the t*Q term runs: true = three ALU-pipe instructions (shift/add), false = one IMAD on the
 // FMA-heavy pipe.  Both pipes issue 16 lanes/cycle per SM sub-partition, so the kernels mix the two forms per butterfly
 // stage to balance them (masks below).
-template <bool SOL = false> __device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q) { // [0,2Q)
+// BFHE_SOL_RT: the two shift amounts come from the kernel parameters (DevConst::sol_sh16 / sol_sh11) instead of being literals.  With
+// literal shifts ptxas rewrites the sequence into IMAD / IMAD.SHL with small constants -- back onto the FMA-heavy pipe, which made
+// every round-1 mask measure the same as no mask.  A shift by a run-time amount can only be an SHF on the ALU pipe, and the final
+// 3-input add is an IADD3.
+// Measured in round 2 (profiles/r2_sol_variants.md): with run-time shifts the stages really run on the ALU pipe -- and the throughput
+// kernel gets SLOWER with every stage converted (80.6k -> 74.2k with half of the stages, 66.4k with all): the kernel is bound by
+// instruction issue / dependency latency at two warps per scheduler, not by the FMA-heavy pipe, so one IMAD beats three ALU instructions.
+#ifndef BFHE_SOL_RT
+#define BFHE_SOL_RT 0
+#endif
+// BFHE_ADD3: 2-input adds of the butterflies are written as 3-input adds with a zero that comes from the kernel parameters: ptxas turns
+// plain 2-input adds into IMAD.IADD "to balance the pipes" -- onto the FMA-heavy pipe -- while a 3-input add can only be an IADD3 (ALU).
+// (same measurement: forcing the adds onto the ALU pipe costs 2.6 %, 80.6k -> 78.5k gates/s; off)
+#ifndef BFHE_ADD3
+#define BFHE_ADD3 0
+#endif
+struct SolSh { u32 a, b, z; }; // 16, 11, 0 at run time
+__device__ __forceinline__ SolSh sol_shifts(const DevConst &P) {
+#if BFHE_SOL_RT
+  return SolSh{P.sol_sh16, P.sol_sh11, P.sol_zero};
+#else
+  return SolSh{16, 11, 0};
+#endif
+}
+__device__ __forceinline__ u32 add2(u32 a, u32 b, SolSh sh) {
+#if BFHE_ADD3
+  return a + b + sh.z;
+#else
+  return a + b;
+#endif
+}
+__device__ __forceinline__ u32 sol_tail(u32 xw, u32 t, SolSh sh) { // xw - t*Q for Q = 2^27 - 2^11 + 1
+  const u32 s = add2(t, 0u - (t << sh.a), sh);
+  return (xw - t) + (s << sh.b);
+}
+template <bool SOL = false> __device__ __forceinline__ u32 mul_shoup(u32 x, u32 w, u32 ws, u32 Q, SolSh sh = SolSh{16, 11, 0}) { // [0,2Q)
   const u32 t = __umulhi(x, ws);
   if constexpr (SOL && BFHE_SOLINAS_Q) {
-    // (written as shifts; nvcc is free to turn them back into IMADs with small constants -- measured fastest that way)
-    const u32 s = t - (t << 16);
-    return (x * w - t) + (s << 11); // x*w - t*Q
+    return sol_tail(x * w, t, sh);
   } else {
     return x * w - t * Q;
   }
@@ -151,7 +184,7 @@ __device__ __forceinline__ u32 comp4(const uint4 &v, int i) { return i == 0 ? v.
 template <int E, bool UNI, int SOLMASK = 0, bool STREAM = false, bool PRE = false>
 __device__ __forceinline__ void ct_pass(u32 (&x)[E], const u32 *__restrict__ utw, const u32 *__restrict__ utws,
                                         const u32 (&w)[E], const u32 (&ws)[E], u32 Q, u32 Q2, const u32 *tab = nullptr,
-                                        const u32 *tabs = nullptr, int lane = 0, const u32 *pre = nullptr) {
+                                        const u32 *tabs = nullptr, int lane = 0, const u32 *pre = nullptr, SolSh sh = SolSh{16, 11, 0}) {
   int si = 0;
   uint4 cw = make_uint4(0, 0, 0, 0), cws = cw;
 #pragma unroll
@@ -174,9 +207,9 @@ __device__ __forceinline__ void ct_pass(u32 (&x)[E], const u32 *__restrict__ utw
         const int a = gi * 2 * t + j, b = a + t;
         u32 T;
         if (PRE && si == 0) T = pre[j];
-        else T = sol ? mul_shoup<true>(x[b], ww, wws, Q) : mul_shoup<false>(x[b], ww, wws, Q);
+        else T = sol ? mul_shoup<true>(x[b], ww, wws, Q, sh) : mul_shoup<false>(x[b], ww, wws, Q);
         x[b] = x[a] - T + Q2;
-        x[a] = x[a] + T;
+        x[a] = add2(x[a], T, sh);
       }
     }
   }
@@ -192,7 +225,7 @@ template <int E, int T, int B, bool UNI, int MAXLAST, int SOLMASK = 0, int SI = 
   static constexpr int OUTB = RED ? 2 : NB;
   __device__ __forceinline__ static void run(u32 (&x)[E], const u32 *__restrict__ utw, const u32 *__restrict__ utws,
                                              const u32 (&w)[E], const u32 (&ws)[E], u32 Q, u32 mu, const u32 *tab = nullptr,
-                                             const u32 *tabs = nullptr, int lane = 0) {
+                                             const u32 *tabs = nullptr, int lane = 0, SolSh sh = SolSh{16, 11, 0}) {
     static_assert(B <= 16, "GS input bound too large");
     const u32 off = B * Q;
     uint4 cw = make_uint4(0, 0, 0, 0), cws = cw;
@@ -211,13 +244,13 @@ template <int E, int T, int B, bool UNI, int MAXLAST, int SOLMASK = 0, int SI = 
 #pragma unroll
       for (int j = 0; j < T; j++) {
         const int a = gi * 2 * T + j, b = a + T;
-        u32 S = x[a] + x[b];
+        u32 S = add2(x[a], x[b], sh);
         u32 D = x[a] - x[b] + off;
-        x[b] = mul_shoup<((SOLMASK >> SI) & 1) != 0>(D, ww, wws, Q);
+        x[b] = mul_shoup<((SOLMASK >> SI) & 1) != 0>(D, ww, wws, Q, sh);
         x[a] = RED ? lazy_reduce(S, Q, mu) : S;
       }
     }
-    if constexpr (!LAST) GsRun<E, 2 * T, OUTB, UNI, MAXLAST, SOLMASK, SI + 1, STREAM>::run(x, utw, utws, w, ws, Q, mu, tab, tabs, lane);
+    if constexpr (!LAST) GsRun<E, 2 * T, OUTB, UNI, MAXLAST, SOLMASK, SI + 1, STREAM>::run(x, utw, utws, w, ws, Q, mu, tab, tabs, lane, sh);
   }
 };
 // bound (in units of Q) of the values GsRun<E,1,B0,*,MAXLAST> leaves behind
@@ -245,8 +278,9 @@ __device__ __forceinline__ void ntt_forward(u32 (&x)[(1 << LOGN) / 32], u32 *buf
                                             const u32 *pre = nullptr) {
   constexpr int E = (1 << LOGN) / 32;
   const u32 Q = P.Q, Q2 = P.Q2;
+  const SolSh sh = sol_shifts(P);
   u32 w[E], ws[E];
-  ct_pass<E, true, SOLW, false, PRE>(x, P.tw, P.tws, w, ws, Q, Q2, nullptr, nullptr, 0, pre);
+  ct_pass<E, true, SOLW, false, PRE>(x, P.tw, P.tws, w, ws, Q, Q2, nullptr, nullptr, 0, pre, sh);
   if constexpr (LOGN & 1) { // span-16 stage across lanes (lane bit 4): group index = k, twiddle psi_br[16+k]
     const bool up = lane & 16;
 #pragma unroll
@@ -261,11 +295,11 @@ __device__ __forceinline__ void ntt_forward(u32 (&x)[(1 << LOGN) / 32], u32 *buf
   __syncwarp();
   row_load<E>(buf, x, lane);
   if constexpr (BFHE_STREAM_TW) {
-    ct_pass<E, false, SOLN, true>(x, P.tw, P.tws, w, ws, Q, Q2, tt.fw, tt.fws, lane);
+    ct_pass<E, false, SOLN, true>(x, P.tw, P.tws, w, ws, Q, Q2, tt.fw, tt.fws, lane, nullptr, sh);
   } else {
     load_lane_tw<E>(tt.fw, w, lane);
     load_lane_tw<E>(tt.fws, ws, lane);
-    ct_pass<E, false, SOLN>(x, P.tw, P.tws, w, ws, Q, Q2);
+    ct_pass<E, false, SOLN>(x, P.tw, P.tws, w, ws, Q, Q2, nullptr, nullptr, 0, nullptr, sh);
   }
 }
 
@@ -277,17 +311,18 @@ __device__ __forceinline__ void ntt_forward2(u32 (&xa)[(1 << LOGN) / 32], u32 (&
   constexpr int E = (1 << LOGN) / 32;
   static_assert((LOGN & 1) == 0, "even log2 N only");
   const u32 Q = P.Q, Q2 = P.Q2;
+  const SolSh sh = sol_shifts(P);
   u32 w[E], ws[E];
-  ct_pass<E, true, SOLW, false, PRE>(xa, P.tw, P.tws, w, ws, Q, Q2, nullptr, nullptr, 0, prea);
-  ct_pass<E, true, SOLW, false, PRE>(xb, P.tw, P.tws, w, ws, Q, Q2, nullptr, nullptr, 0, preb);
+  ct_pass<E, true, SOLW, false, PRE>(xa, P.tw, P.tws, w, ws, Q, Q2, nullptr, nullptr, 0, prea, sh);
+  ct_pass<E, true, SOLW, false, PRE>(xb, P.tw, P.tws, w, ws, Q, Q2, nullptr, nullptr, 0, preb, sh);
   __syncwarp();
   col_store<E>(bufa, xa, lane);
   col_store<E>(bufb, xb, lane);
   __syncwarp();
   row_load<E>(bufa, xa, lane);
   row_load<E>(bufb, xb, lane);
-  ct_pass<E, false, SOLN, true>(xa, P.tw, P.tws, w, ws, Q, Q2, tt.fw, tt.fws, lane);
-  ct_pass<E, false, SOLN, true>(xb, P.tw, P.tws, w, ws, Q, Q2, tt.fw, tt.fws, lane);
+  ct_pass<E, false, SOLN, true>(xa, P.tw, P.tws, w, ws, Q, Q2, tt.fw, tt.fws, lane, nullptr, sh);
+  ct_pass<E, false, SOLN, true>(xb, P.tw, P.tws, w, ws, Q, Q2, tt.fw, tt.fws, lane, nullptr, sh);
 }
 
 // inverse (unscaled: N * true value; the keys carry N^-1): x in row layout (evaluation form, values < B0*Q)
@@ -296,14 +331,15 @@ template <int LOGN, int B0, int SOLN = 0, int SOLW = 0>
 __device__ __forceinline__ void ntt_inverse(u32 (&x)[(1 << LOGN) / 32], u32 *buf, const DevConst &P, const TwTabs &tt, int lane) {
   constexpr int E = (1 << LOGN) / 32;
   const u32 Q = P.Q, mu = P.mu;
+  const SolSh sh = sol_shifts(P);
   u32 w[E], ws[E];
   constexpr int ML = (LOGN & 1) ? 8 : 16; // what the next stage can take
   if constexpr (BFHE_STREAM_TW) {
-    GsRun<E, 1, B0, false, ML, SOLN, 0, true>::run(x, P.itw, P.itws, w, ws, Q, mu, tt.iw, tt.iws, lane);
+    GsRun<E, 1, B0, false, ML, SOLN, 0, true>::run(x, P.itw, P.itws, w, ws, Q, mu, tt.iw, tt.iws, lane, sh);
   } else {
     load_lane_tw<E>(tt.iw, w, lane);
     load_lane_tw<E>(tt.iws, ws, lane);
-    GsRun<E, 1, B0, false, ML, SOLN>::run(x, P.itw, P.itws, w, ws, Q, mu);
+    GsRun<E, 1, B0, false, ML, SOLN>::run(x, P.itw, P.itws, w, ws, Q, mu, nullptr, nullptr, 0, sh);
   }
   constexpr int B1 = gs_out_bound(E, B0, ML);
   __syncwarp();
@@ -322,9 +358,9 @@ __device__ __forceinline__ void ntt_inverse(u32 (&x)[(1 << LOGN) / 32], u32 *buf
       x[k] = up ? mul_shoup(D, P.itw[16 + k], P.itws[16 + k], Q) : (x[k] + o);
     }
     constexpr int B2 = 2 * B1;
-    GsRun<E, 1, B2, true, 32, SOLW>::run(x, P.itw, P.itws, w, ws, Q, mu);
+    GsRun<E, 1, B2, true, 32, SOLW>::run(x, P.itw, P.itws, w, ws, Q, mu, nullptr, nullptr, 0, sh);
   } else {
-    GsRun<E, 1, B1, true, 32, SOLW>::run(x, P.itw, P.itws, w, ws, Q, mu);
+    GsRun<E, 1, B1, true, 32, SOLW>::run(x, P.itw, P.itws, w, ws, Q, mu, nullptr, nullptr, 0, sh);
   }
 #pragma unroll
   for (int k = 0; k < E; k++) x[k] = csub(lazy_reduce(x[k], Q, mu), Q);

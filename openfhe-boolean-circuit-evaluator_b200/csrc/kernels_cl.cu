@@ -30,13 +30,15 @@ constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, NPAD =
 constexpr int KEYPOLYS = 2 * ROWS * 2;
 constexpr u32 DIGIT_OFF = 64u + (64u << 7) + (64u << 14) + (64u << 21);
 constexpr u32 SOLINAS_Q = (1u << 27) - (1u << 11) + 1;
-constexpr u32 KEYBYTES = (u32)KEYPOLYS * NB * 4;   // 32 KB per CTA and step
 constexpr u32 RECV_TX = (u32)(R - 1) * 2 * NB * 4; // bytes the three peers push into a CTA per step
 
-// per-rank twiddle block (host-generated, engine.cu clx_tables): fw | fws | iw | iws, each TWW words:
-//   [0, 8)                 pass A (register stages across the 32-strided values), uniform over the warp: w[1], w[2..3], w[4..7]
-//   [8 + 256 s, + 256)     s = 0: pass B register stages, s = 1 / 2: the two shuffle stages; each [chunk 2][lane 32][4] (8 per lane)
-constexpr int TWW = 8 + 3 * 256;
+// per-rank twiddle block (host-generated, engine.cu): fw[TWF] | fws[TWF] | iw[TWI] | iws[TWI]
+//   fw:  [0, 8)            pass A (register stages across the 32-strided values), uniform over the warp: w[1], w[2..3], w[4..7]
+//        [8, 264)          pass B (lane = 4 blk + q holds positions 32 blk + q + 4 m), [chunk 2][lane 32][4]: w[1], w[2..3], w[4..7] per lane
+//        [264, 520)        pass C (lane holds positions 8 lane .. 8 lane + 7), same layout: w[2..3], w[4..7] per lane
+//   iw:  [0, 8)            inverse pass A, uniform
+//        [8 + 256 s, ..)   s = 0..4: the inverse stage with half-size 2^s for MAC slot t (the five stages done by shuffles), [t]
+constexpr int TWF = 8 + 2 * 256, TWI = 8 + 5 * 256, TWR = 2 * TWF + 2 * TWI;
 
 __device__ __forceinline__ u32 redc(u64 s, u32 Q, u32 qinv_neg) { // s * 2^-32 mod Q, lazy
   const u32 m = (u32)s * qinv_neg;
@@ -115,29 +117,17 @@ template <int T, int B> struct Gs8 {
     }
   }
 };
-template <int B> struct GsShfl { // one stage across lanes `mask` apart; the upper lane holds b
+template <int B> struct GsShfl1 { // one inverse stage across lanes `mask` apart on ONE value per thread; the upper lane holds b
   static constexpr bool RED = (2 * B > 16);
   static constexpr int OUTB = RED ? 2 : 2 * B;
-  __device__ __forceinline__ static void run(u32 (&x)[8], const u32 (&w)[8], const u32 (&ws)[8], u32 Q, int mask, bool upper) {
+  __device__ __forceinline__ static u32 run(u32 x, u32 w, u32 ws, u32 Q, int mask, bool upper) {
     static_assert(B <= 16, "GS input bound too large");
-#pragma unroll
-    for (int m = 0; m < 8; m++) {
-      const u32 o = __shfl_xor_sync(0xffffffffu, x[m], mask);
-      const u32 D = o - x[m] + B * Q; // upper lane: (lower - upper) * w
-      const u32 pr = mul_shoup(D, w[m], ws[m], Q);
-      const u32 S = x[m] + o;
-      x[m] = upper ? pr : (RED ? lazy_reduce(S, Q) : S);
-    }
+    const u32 o = __shfl_xor_sync(0xffffffffu, x, mask);
+    const u32 pr = mul_shoup(o - x + B * Q, w, ws, Q); // upper lane: (lower - upper) * w
+    const u32 S = x + o;
+    return upper ? pr : (RED ? lazy_reduce(S, Q) : S);
   }
 };
-__device__ __forceinline__ void ct_shfl(u32 (&x)[8], const u32 (&w)[8], const u32 (&ws)[8], u32 Q, u32 Q2, int mask, bool upper) {
-#pragma unroll
-  for (int m = 0; m < 8; m++) {
-    const u32 v = upper ? mul_shoup(x[m], w[m], ws[m], Q) : x[m];
-    const u32 o = __shfl_xor_sync(0xffffffffu, v, mask);
-    x[m] = upper ? (o - v + Q2) : (v + o);
-  }
-}
 __device__ __forceinline__ void load8(const u32 *tab, u32 (&w)[8], int lane) { // [chunk 2][lane 32][4]
   const uint4 a = reinterpret_cast<const uint4 *>(tab)[lane], b = reinterpret_cast<const uint4 *>(tab)[32 + lane];
   w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
@@ -147,22 +137,17 @@ __device__ __forceinline__ void load8(const u32 *tab, u32 (&w)[8], int lane) { /
 __device__ __forceinline__ int rowpos(int i) { return (i & ~31) | ((i + 4 * (i >> 5)) & 31); }
 
 // in-place position (0 .. N-1, Cooley-Tukey order: slot P holds the evaluation at psi^(2 bitrev(P) + 1)) of MAC slot t of CTA k
-__host__ __device__ __forceinline__ int slot_position(int k, int t) {
-  const int lane = t >> 3, m = t & 7, blk = lane >> 2, q = lane & 3;
-  return NB * k + 32 * blk + q + 4 * m;
-}
+__host__ __device__ __forceinline__ int slot_position(int k, int t) { return NB * k + t; }
 
 struct Smem { // word offsets
   static constexpr int rbuf = 0;                              // [parity 2][source CTA R][component 2][NB]
   static constexpr int dct = rbuf + 2 * R * 2 * NB;           // [ROWS][NB]
   static constexpr int prod = dct + ROWS * NB;                // [2][NB]
-  static constexpr int key = prod + 2 * NB;                   // [parity 2][KEYPOLYS][NB]
-  static constexpr int tw = key + 2 * KEYPOLYS * NB;          // fw | fws | iw | iws, TWW words each (padded to a multiple of 4)
-  static constexpr int lut = tw + 4 * ((TWW + 3) & ~3);       // [3][128][32]
+  static constexpr int lut = prod + 2 * NB;                   // [3][128][32]
   static constexpr int F = lut + 3 * 128 * 32;                // [2N]
   static constexpr int idx = F + 2 * N;                       // u16 [NPAD]
-  static constexpr int bars = idx + NPAD / 2;                 // kbar[2], rbar[2]
-  static constexpr int words = bars + 8;
+  static constexpr int bars = idx + NPAD / 2;                 // rbar[2]
+  static constexpr int words = bars + 4;
   static constexpr size_t bytes = (size_t)words * 4;
 };
 
@@ -171,10 +156,9 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
                         const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   u32 *sm = reinterpret_cast<u32 *>(smem_raw);
-  u32 *rbuf = sm + Smem::rbuf, *dct = sm + Smem::dct, *prod = sm + Smem::prod, *s_key = sm + Smem::key, *s_tw = sm + Smem::tw;
-  u32 *s_lut = sm + Smem::lut, *s_F = sm + Smem::F;
+  u32 *rbuf = sm + Smem::rbuf, *dct = sm + Smem::dct, *prod = sm + Smem::prod, *s_lut = sm + Smem::lut, *s_F = sm + Smem::F;
   u16 *s_idx = reinterpret_cast<u16 *>(sm + Smem::idx);
-  u64 *kbar = reinterpret_cast<u64 *>(sm + Smem::bars), *rbar = kbar + 2;
+  u64 *rbar = reinterpret_cast<u64 *>(sm + Smem::bars);
   __shared__ u32 s_b;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -182,13 +166,11 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   const size_t gi = blockIdx.x / R;
   const u32 Q = P.Q, Q2 = P.Q2, q = P.q, n = P.n, qinv = P.qinv_neg;
   const DevGate dg = gates[gi];
-  constexpr int TWP = (TWW + 3) & ~3;
 
   if (tid == 0) {
-    mbar_init(kbar + 0, 1); mbar_init(kbar + 1, 1); mbar_init(rbar + 0, 1); mbar_init(rbar + 1, 1);
+    mbar_init(rbar + 0, 1); mbar_init(rbar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 4 * TWP; i += THREADS) s_tw[i] = g_tw[(size_t)k * 4 * TWP + i];
   for (int i = tid; i < 2 * N; i += THREADS) s_F[i] = g_F[i];
   { // look-up tables of the two cross-block forward stages for block k: y_k = d0 + c1 d2 + c2 d1 + c3 d3 with
     //   k = 0: (+w1, +w2, +w2 w1)   k = 1: (+w1, -w2, -w2 w1)   k = 2: (-w1, +w3, -w3 w1)   k = 3: (-w1, -w3, +w3 w1)
@@ -225,20 +207,6 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   }
   __syncthreads();
 
-  auto issue_keys = [&](u32 step) { // thread 0: this CTA's 32 KB of step `step`: [step][rank][polynomial][NB] contiguous
-    u64 *bar = kbar + (step & 1);
-    mbar_expect_tx(bar, KEYBYTES);
-    const u32 *src = bkx + ((size_t)step * R + k) * KEYPOLYS * NB;
-    u32 *dst = s_key + (size_t)(step & 1) * KEYPOLYS * NB;
-    bulk_g2s(dst, src, 16384, bar);
-    bulk_g2s(dst + 4096, src + 4096, 16384, bar);
-  };
-  static_assert(KEYBYTES == 2 * 16384, "two bulk copies");
-  if (tid == 0 && n > 0) {
-    issue_keys(0);
-    if (n > 1) issue_keys(1);
-  }
-
   // accumulator: thread t holds coefficients t + 256 i1 (i1 = 0..3) of both components, canonical [0, Q)
   u32 acc[2][4];
   {
@@ -259,9 +227,16 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   }
   cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
 
-  // per-thread constants
+  // ---- per-thread constants, kept in registers for the whole blind rotation ----
   const u32 ex = 2 * (__brev((u32)slot_position((int)k, tid)) >> (32 - LOGN)) + 1; // MAC slot tid evaluates at psi^ex
-  const u32 *fw = s_tw, *fws = s_tw + TWP, *iw = s_tw + 2 * TWP, *iws = s_tw + 3 * TWP;
+  const u32 *twr = g_tw + (size_t)k * TWR, *g_fw = twr, *g_fws = twr + TWF, *g_iw = twr + 2 * TWF, *g_iws = twr + 2 * TWF + TWI;
+  u32 fA[8], fAs[8], fB[8], fBs[8], fC[8], fCs[8], iA[8], iAs[8], iS[5], iSs[5];
+#pragma unroll
+  for (int p = 0; p < 8; p++) { fA[p] = g_fw[p]; fAs[p] = g_fws[p]; iA[p] = g_iw[p]; iAs[p] = g_iws[p]; }
+  load8(g_fw + 8, fB, lane); load8(g_fws + 8, fBs, lane);
+  load8(g_fw + 8 + 256, fC, lane); load8(g_fws + 8 + 256, fCs, lane);
+#pragma unroll
+  for (int s5 = 0; s5 < 5; s5++) { iS[s5] = g_iw[8 + 256 * s5 + tid]; iSs[s5] = g_iws[8 + 256 * s5 + tid]; }
   const u32 iw1 = P.itw[1], iw1s = P.itws[1], iwb = P.itw[2], iwbs = P.itws[2], iwc = P.itw[3], iwcs = P.itws[3];
   const int blk = lane >> 2, qq = lane & 3;
   u32 peer_rbuf[R - 1], peer_bar[R - 1]; // shared::cluster addresses in the three peers (receive buffer, rbar[0]; rbar[1] is 8 bytes on)
@@ -271,10 +246,26 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     peer_rbuf[p] = dsmem_addr(rbuf, dest);
     peer_bar[p] = dsmem_addr(rbar, dest);
   }
+  // this CTA's quarter of the key, word `tid` of each of the 32 polynomials of a step: [step][rank][polynomial][NB]
+  const u32 *kbase = bkx + (size_t)k * KEYPOLYS * NB + tid;
 
+#ifdef BFHE_PHASE_TIMING
+  long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tc0 = clock64(), tc1;
+#define CLX_T(i) do { tc1 = clock64(); tph[i] += tc1 - tc0; tc0 = tc1; } while (0)
+#else
+#define CLX_T(i)
+#endif
   for (u32 step = 0; step < n; step++) {
     const u32 par = step & 1;
     if (tid == 0) mbar_expect_tx(rbar + par, RECV_TX); // this step's receive expectation (early pushes merely run the count negative)
+    // the step's key words go straight from L2 into registers; the loads are in flight during phases A and B (no staging buffer, no
+    // mbarrier: the round-1 cluster kernels spent ~200-400 cycles per step issuing and waiting for their TMA key tile)
+    u32 kreg[KEYPOLYS];
+    {
+      const u32 *kp = kbase + (size_t)step * R * KEYPOLYS * NB;
+#pragma unroll
+      for (int pl = 0; pl < KEYPOLYS; pl++) kreg[pl] = __ldg(kp + pl * NB);
+    }
     // ---- phase A: digits of the accumulator -> block k of the two cross-block forward stages, by table look-up ----
 #pragma unroll
     for (int c = 0; c < 2; c++) {
@@ -289,41 +280,39 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
         dct[(c + 2 * l) * NB + rowpos(tid)] = y; // lazy, < 4Q + 64
       }
     }
+    CLX_T(0);
     __syncthreads();
-    // ---- phase B: warp w transforms row w (256 points, 8 per lane) ----
+    CLX_T(1);
+    // ---- phase B: warp w transforms row w (256 points, 8 per lane): 3 + 3 + 2 register stages, two in-place transposes ----
     {
       u32 *row = dct + warp * NB;
-      u32 x[8], w[8], ws[8];
+      u32 x[8];
 #pragma unroll
       for (int m = 0; m < 8; m++) x[m] = row[rowpos(lane + 32 * m)];
-#pragma unroll
-      for (int p = 1; p < 8; p++) { w[p] = fw[p]; ws[p] = fws[p]; } // uniform over the warp
-      ct8_stage<4>(x, w, ws, Q, Q2); ct8_stage<2>(x, w, ws, Q, Q2); ct8_stage<1>(x, w, ws, Q, Q2);
-      __syncwarp();
+      ct8_stage<4>(x, fA, fAs, Q, Q2); ct8_stage<2>(x, fA, fAs, Q, Q2); ct8_stage<1>(x, fA, fAs, Q, Q2);
 #pragma unroll
       for (int m = 0; m < 8; m++) row[rowpos(lane + 32 * m)] = x[m];
       __syncwarp();
 #pragma unroll
       for (int m = 0; m < 8; m++) x[m] = row[rowpos(32 * blk + qq + 4 * m)];
-      load8(fw + 8, w, lane); load8(fws + 8, ws, lane);
-      ct8_stage<4>(x, w, ws, Q, Q2); ct8_stage<2>(x, w, ws, Q, Q2); ct8_stage<1>(x, w, ws, Q, Q2);
-      load8(fw + 8 + 256, w, lane); load8(fws + 8 + 256, ws, lane);
-      ct_shfl(x, w, ws, Q, Q2, 2, (qq & 2) != 0);
-      load8(fw + 8 + 512, w, lane); load8(fws + 8 + 512, ws, lane);
-      ct_shfl(x, w, ws, Q, Q2, 1, (qq & 1) != 0);
+      ct8_stage<4>(x, fB, fBs, Q, Q2); ct8_stage<2>(x, fB, fBs, Q, Q2); ct8_stage<1>(x, fB, fBs, Q, Q2);
+#pragma unroll
+      for (int m = 0; m < 8; m++) row[rowpos(32 * blk + qq + 4 * m)] = x[m];
       __syncwarp();
-      *reinterpret_cast<uint4 *>(row + 8 * lane) = make_uint4(x[0], x[1], x[2], x[3]); // MAC slot 8 lane + m
+      {
+        const uint4 a = *reinterpret_cast<const uint4 *>(row + rowpos(8 * lane)), b = *reinterpret_cast<const uint4 *>(row + rowpos(8 * lane + 4));
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      }
+      ct8_stage<2>(x, fC, fCs, Q, Q2); ct8_stage<1>(x, fC, fCs, Q, Q2);
+      __syncwarp(); // every lane has read its pass-C inputs before the row is overwritten in slot order
+      *reinterpret_cast<uint4 *>(row + 8 * lane) = make_uint4(x[0], x[1], x[2], x[3]); // MAC slot t = position t
       *reinterpret_cast<uint4 *>(row + 8 * lane + 4) = make_uint4(x[4], x[5], x[6], x[7]);
     }
+    CLX_T(2);
     __syncthreads();
-    if (tid == 0 && step >= 1 && step + 1 < n) { // the key buffer of parity (step + 1) & 1 was last read by the product of step - 1
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue_keys(step + 1);
-    }
-    // ---- phase C: external product on my 256 slots, one slot per thread ----
-    mbar_wait(kbar + par, (step >> 1) & 1);
+    CLX_T(3);
+    // ---- phase C: external product on my 256 slots, one slot per thread, then the five inverse stages that stay inside a warp ----
     {
-      const u32 *kt = s_key + (size_t)par * KEYPOLYS * NB + tid;
       const u32 m = s_idx[step];
       const u32 y = m * ex, ny = 0u - y;
       const u32 fp = s_F[f_index(y)], fn = s_F[f_index(ny)]; // (X^m - 1), (X^-m - 1) at this slot, Montgomery form
@@ -333,46 +322,38 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
         const u32 d = dct[rw * NB + tid];
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
-          sp[cc] += (u64)d * kt[((0 * ROWS + rw) * 2 + cc) * NB];
-          sn[cc] += (u64)d * kt[((1 * ROWS + rw) * 2 + cc) * NB];
+          sp[cc] += (u64)d * kreg[(0 * ROWS + rw) * 2 + cc];
+          sn[cc] += (u64)d * kreg[(1 * ROWS + rw) * 2 + cc];
         }
       }
+      CLX_T(4);
 #pragma unroll
-      for (int cc = 0; cc < 2; cc++)
-        prod[cc * NB + tid] = redc((u64)redc(sp[cc], Q, qinv) * fp + (u64)redc(sn[cc], Q, qinv) * fn, Q, qinv); // < 2Q
-    }
-    __syncthreads();
-    // ---- phase D: warps 0 / 1: inverse sub-transform of product component 0 / 1, push the partial values to the peers ----
-    if (warp < 2) {
-      u32 x[8], w[8], ws[8];
-      const u32 *pr = prod + warp * NB;
-      {
-        const uint4 a = *reinterpret_cast<const uint4 *>(pr + 8 * lane), b = *reinterpret_cast<const uint4 *>(pr + 8 * lane + 4);
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      for (int cc = 0; cc < 2; cc++) {
+        u32 v = redc((u64)redc(sp[cc], Q, qinv) * fp + (u64)redc(sn[cc], Q, qinv) * fn, Q, qinv); // < 2Q
+        using T0 = GsShfl1<2>; using T1 = GsShfl1<T0::OUTB>; using T2 = GsShfl1<T1::OUTB>; using T3 = GsShfl1<T2::OUTB>; using T4 = GsShfl1<T3::OUTB>;
+        v = T0::run(v, iS[0], iSs[0], Q, 1, (lane & 1) != 0);
+        v = T1::run(v, iS[1], iSs[1], Q, 2, (lane & 2) != 0);
+        v = T2::run(v, iS[2], iSs[2], Q, 4, (lane & 4) != 0);
+        v = T3::run(v, iS[3], iSs[3], Q, 8, (lane & 8) != 0);
+        v = T4::run(v, iS[4], iSs[4], Q, 16, (lane & 16) != 0);
+        static_assert(T4::OUTB == 4, "bound of the values handed to the last three inverse stages");
+        prod[cc * NB + tid] = v;
       }
-      load8(iw + 8 + 512, w, lane); load8(iws + 8 + 512, ws, lane);
-      using S7 = GsShfl<2>;
-      S7::run(x, w, ws, Q, 1, (qq & 1) != 0);
-      load8(iw + 8 + 256, w, lane); load8(iws + 8 + 256, ws, lane);
-      using S6 = GsShfl<S7::OUTB>;
-      S6::run(x, w, ws, Q, 2, (qq & 2) != 0);
-      load8(iw + 8, w, lane); load8(iws + 8, ws, lane);
-      using S5 = Gs8<1, S6::OUTB>; using S4 = Gs8<2, S5::OUTB>; using S3 = Gs8<4, S4::OUTB>;
-      S5::run(x, w, ws, Q); S4::run(x, w, ws, Q); S3::run(x, w, ws, Q);
-      u32 *row = dct + warp * NB; // scratch for the transpose (rows 0 / 1 are dead after the product)
+    }
+    CLX_T(5);
+    __syncthreads();
+    CLX_T(6);
+    // ---- phase D: warps 0 / 1: the last three inverse stages of product component 0 / 1; push the partial values to the peers ----
+    if (warp < 2) {
+      u32 x[8];
+      const u32 *pr = prod + warp * NB;
 #pragma unroll
-      for (int m = 0; m < 8; m++) row[rowpos(32 * blk + qq + 4 * m)] = x[m];
-      __syncwarp();
-#pragma unroll
-      for (int m = 0; m < 8; m++) x[m] = row[rowpos(lane + 32 * m)];
-#pragma unroll
-      for (int p = 1; p < 8; p++) { w[p] = iw[p]; ws[p] = iws[p]; }
-      using S2 = Gs8<1, S3::OUTB>; using S1 = Gs8<2, S2::OUTB>; using S0 = Gs8<4, S1::OUTB>;
-      S2::run(x, w, ws, Q); S1::run(x, w, ws, Q); S0::run(x, w, ws, Q);
+      for (int m = 0; m < 8; m++) x[m] = pr[lane + 32 * m];
+      using S2 = Gs8<1, 4>; using S1 = Gs8<2, S2::OUTB>; using S0 = Gs8<4, S1::OUTB>;
+      S2::run(x, iA, iAs, Q); S1::run(x, iA, iAs, Q); S0::run(x, iA, iAs, Q);
       static_assert(S0::OUTB <= 4, "partial values must stay below 4Q for the cross-block stages");
       // my own copy, natural order j = lane + 32 m; then 16-byte pushes of 4 consecutive j to the three peers
       u32 *mine = rbuf + ((par * R + k) * 2 + warp) * NB;
-      __syncwarp();
 #pragma unroll
       for (int m = 0; m < 8; m++) mine[lane + 32 * m] = x[m];
       __syncwarp();
@@ -384,8 +365,10 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
         st_async4(peer_rbuf[p] + off + 512u, v1, peer_bar[p] + 8u * par);
       }
     }
+    CLX_T(7);
     __syncthreads(); // my own partial values are visible to all my warps
     mbar_wait(rbar + par, (step >> 1) & 1); // ... and the peers' have landed
+    CLX_T(8);
     // ---- phase E: the two cross-block inverse stages for coefficients tid + 256 i1, both components; accumulate ----
 #pragma unroll
     for (int c = 0; c < 2; c++) {
@@ -400,6 +383,7 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
       acc[c][2] = csub(acc[c][2] + csub(x2, Q), Q);
       acc[c][3] = csub(acc[c][3] + csub(x3, Q), Q);
     }
+    CLX_T(9);
   }
 
   // ---- epilogue: sample extraction (a14) and ModSwitch Q -> qKS (a15); CTA k writes the coefficients tid + 256 k ----
@@ -418,6 +402,10 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
       if (j == 0) e[N] = modswitch(csub(acc[1][i1] + P.Q8, Q));
     }
   }
+#ifdef BFHE_PHASE_TIMING
+  if (acc_dbg && lane == 0 && (warp == 0 || warp == 7))
+    for (int i = 0; i < 10; i++) acc_dbg[(gi * 2 + 1) * N + NB * k + 32 + 16 * (warp == 7) + i] = (u32)(tph[i] / 1000); // kilo-cycles
+#endif
   cluster_sync_all(); // a CTA must not exit while its peers may still push into its shared memory
 }
 
@@ -437,7 +425,7 @@ __global__ void bk_slice_clx_kernel(const u32 *__restrict__ src, u32 *__restrict
 bool clx_supported(const DevConst &P, int method_ap) {
   return !method_ap && P.N == 1024 && P.dG == 4 && P.logBG == 7 && P.Q == clx::SOLINAS_Q && P.n <= (u32)clx::NPAD;
 }
-size_t clx_tw_words() { return (size_t)clx::R * 4 * ((clx::TWW + 3) & ~3); }
+size_t clx_tw_words() { return (size_t)clx::R * clx::TWR; }
 static int clx_device_slot() {
   int dev = 0;
   cudaGetDevice(&dev);

@@ -71,8 +71,8 @@ def ref_inv_unscaled(a):
     return a
 
 
-def tables(k, inv):
-    T = ITW if inv else TW
+def tables_fwd(k):
+    T = TW
     A = [0] * 8
     A[1] = T[4 + k]
     for g in range(2):
@@ -80,19 +80,29 @@ def tables(k, inv):
     for g in range(4):
         A[4 + g] = T[16 + 4 * k + g]
     B = np.zeros((32, 8), dtype=object)
-    S6 = np.zeros((32, 8), dtype=object)
-    S7 = np.zeros((32, 8), dtype=object)
+    C = np.zeros((32, 8), dtype=object)
     for lane in range(32):
-        blk, q = lane >> 2, lane & 3
+        blk = lane >> 2
         B[lane][1] = T[32 + 8 * k + blk]
         for g in range(2):
             B[lane][2 + g] = T[64 + 16 * k + 2 * blk + g]
+            C[lane][2 + g] = T[256 + 64 * k + 2 * lane + g]
         for g in range(4):
             B[lane][4 + g] = T[128 + 32 * k + 4 * blk + g]
-        for m in range(8):
-            S6[lane][m] = T[256 + 64 * k + 8 * blk + m]
-            S7[lane][m] = T[512 + 128 * k + 16 * blk + 2 * m + (q >> 1)]
-    return A, B, S6, S7
+            C[lane][4 + g] = T[512 + 128 * k + 4 * lane + g]
+    return A, B, C
+
+
+def tables_inv(k):
+    T = ITW
+    A = [0] * 8
+    A[1] = T[4 + k]
+    for g in range(2):
+        A[2 + g] = T[8 + 2 * k + g]
+    for g in range(4):
+        A[4 + g] = T[16 + 4 * k + g]
+    S = [[T[(512 >> s) + ((256 * k + t) >> (s + 1))] for t in range(NB)] for s in range(5)]
+    return A, S
 
 
 def ct8(x, w, T):
@@ -113,8 +123,8 @@ def gs8(x, w, T):
 
 
 def sub_fwd(k, y):
-    """y[256]: block k after the two cross-block stages.  Returns slots[t], t = 8 lane + m (the MAC order)."""
-    A, B, S6, S7 = tables(k, False)
+    """y[256]: block k after the two cross-block stages.  Returns slots[t] = value at in-place position 256 k + t (the MAC order)."""
+    A, B, C = tables_fwd(k)
     row = list(y)
     for lane in range(32):  # pass A
         x = [row[lane + 32 * m] for m in range(8)]
@@ -122,48 +132,35 @@ def sub_fwd(k, y):
             ct8(x, A, T)
         for m in range(8):
             row[lane + 32 * m] = x[m]
-    X = {}
     for lane in range(32):  # pass B
         blk, q = lane >> 2, lane & 3
         x = [row[32 * blk + q + 4 * m] for m in range(8)]
         for T in (4, 2, 1):
             ct8(x, B[lane], T)
-        X[lane] = x
-    for mask, tab, bit in ((2, S6, 2), (1, S7, 1)):  # shuffle stages
-        Y = {}
-        for lane in range(32):
-            upper = bool((lane & 3) & bit)
-            x, o = X[lane], X[lane ^ mask]
-            if upper:
-                Y[lane] = [(o[m] - x[m] * tab[lane][m]) % Q for m in range(8)]
-            else:
-                Y[lane] = [(x[m] + o[m] * tab[lane ^ mask][m]) % Q for m in range(8)]
-        X = Y
-    return [X[t >> 3][t & 7] for t in range(NB)]
+        for m in range(8):
+            row[32 * blk + q + 4 * m] = x[m]
+    for lane in range(32):  # pass C
+        x = [row[8 * lane + j] for j in range(8)]
+        for T in (2, 1):
+            ct8(x, C[lane], T)
+        for j in range(8):
+            row[8 * lane + j] = x[j]
+    return row
 
 
 def sub_inv(k, slots):
-    A, B, S6, S7 = tables(k, True)
-    X = {lane: [slots[8 * lane + m] for m in range(8)] for lane in range(32)}
-    for mask, tab, bit in ((1, S7, 1), (2, S6, 2)):
-        Y = {}
-        for lane in range(32):
-            upper = bool((lane & 3) & bit)
-            x, o = X[lane], X[lane ^ mask]
-            if upper:
-                Y[lane] = [(o[m] - x[m]) * tab[lane][m] % Q for m in range(8)]
-            else:
-                Y[lane] = [(x[m] + o[m]) % Q for m in range(8)]
-        X = Y
-    row = [0] * NB
-    for lane in range(32):
-        blk, q = lane >> 2, lane & 3
-        x = X[lane]
-        for T in (1, 2, 4):
-            gs8(x, B[lane], T)
-        for m in range(8):
-            row[32 * blk + q + 4 * m] = x[m]
-    for lane in range(32):
+    A, S = tables_inv(k)
+    v = list(slots)
+    for s in range(5):  # five stages across the lanes of a warp, one value per thread t
+        mask = 1 << s
+        nv = [0] * NB
+        for t in range(NB):
+            upper = bool(t & mask)
+            x, o = v[t], v[t ^ mask]
+            nv[t] = (o - x) * S[s][t] % Q if upper else (x + o) % Q
+        v = nv
+    row = v
+    for lane in range(32):  # the three widest stages, pass-A layout
         x = [row[lane + 32 * m] for m in range(8)]
         for T in (1, 2, 4):
             gs8(x, A, T)
@@ -173,8 +170,7 @@ def sub_inv(k, slots):
 
 
 def slot_position(k, t):
-    lane, m = t >> 3, t & 7
-    return NB * k + 32 * (lane >> 2) + (lane & 3) + 4 * m
+    return NB * k + t
 
 
 def main():

@@ -21,6 +21,12 @@ for count in [int(a) for a in os.environ.get('COUNTS', '1,148').split(',')]:
         for w in (0, 1):
             print(count, "gates, comp", w, {n: round(float(v), 1) for n, v in zip(names, t[:, w].mean(0))}, "total kcyc", round(float(t[:, w].sum(1).mean()), 1))
         continue
+    if os.environ.get('GPC') == '128':  # slot-sliced cluster kernel: [gate][component 1][256 rank + 32 + 16*(warp==7) + phase]
+        names = ["A lut", "sync1", "B sub-ntt", "sync2", "keywait", "C mac", "sync3", "D intt+push", "sync4+recvwait", "E cross+acc"]
+        for h in (0, 1):
+            t = np.stack([acc[:, 1, 256 * k + 32 + 16 * h:256 * k + 42 + 16 * h] for k in range(4)], 1).astype(np.float64)
+            print(count, "gates, warp", 7 * h, {n: round(float(v), 1) for n, v in zip(names, t.mean((0, 1)))}, "total kcyc", round(float(t.sum(2).mean()), 1))
+        continue
     if os.environ.get('GPC') == '32':  # cluster kernel: [gate][rank][32 + 8*(warp==7) + phase]
         for h in (0, 1):
             t = acc[:, :, 32 + 8 * h:37 + 8 * h].astype(np.float64)
