@@ -79,6 +79,23 @@ int bfhe_import_keys(bfhe_ctx *, const void *buf, size_t len);
 int bfhe_save_keys(const bfhe_ctx *, const char *path, int include_sk);
 int bfhe_load_keys(bfhe_ctx *, const char *path);
 
+/* ---- OpenFHE 1.0.x object exchange (the reference's crypto is find_package(OpenFHE), CMakeLists.txt:8, "Tested with
+ * OpenFHE v.1.0.1", Release_Notes.md:4) ----
+ * cereal JSON archives as OpenFHE's own Serial::SerializeToFile(path, obj, SerType::JSON) writes them (the reference itself never
+ * serialises): the LWE secret key (LWEPrivateKey), the refresh key (cc.GetRefreshKey(), RingGSWACCKey), the switching key
+ * (cc.GetSwitchKey(), LWESwitchingKey) and single LWE ciphertexts.  Refresh-key polynomials are taken in EVALUATION format (OpenFHE's
+ * order: Cooley-Tukey bit-reversed, smallest primitive 2N-th root) or COEFFICIENT format, per polynomial as its "f" member says.
+ * Importing both the refresh and the switching key leaves the context exactly as after bfhe_btkeygen.  A file whose ring modulus is
+ * not this context's Q is refused with BFHE_ERR_FORMAT.  The layout is restated from the 1.0.x sources from
+ * memory -- OpenFHE is not available in this build environment -- so parity against a real OpenFHE file is UNPINNED until a
+ * maintainer runs tools/openfhe_export_keys.cpp (INTEGRATION.md "Closing the parity gap").  cereal's portable-binary form is
+ * positional and cannot be checked offline; it is deliberately not offered. */
+enum { BFHE_OFHE_SECRET_KEY = 0, BFHE_OFHE_REFRESH_KEY = 1, BFHE_OFHE_SWITCH_KEY = 2 };
+int bfhe_import_openfhe_json(bfhe_ctx *, int what, const char *path);
+int bfhe_export_openfhe_json(const bfhe_ctx *, int what, const char *path);
+int bfhe_import_openfhe_ct_json(const bfhe_ctx *, const char *path, uint32_t *ct_row /* ct_stride words */);
+int bfhe_export_openfhe_ct_json(const bfhe_ctx *, const uint32_t *ct_row, const char *path);
+
 /* ---- host-side LWE: Encrypt(sk, bit, FRESH) / Decrypt(sk, ct, &res)  (src/circuit.cpp:506,800; src/gate.cpp:72..) ---- */
 int bfhe_encrypt(const bfhe_ctx *, const uint8_t *bits, size_t count, uint64_t seed, uint32_t *ct_host /* count*ct_stride */);
 int bfhe_decrypt(const bfhe_ctx *, const uint32_t *ct_host, size_t count, uint8_t *out /* floor(4r/q) in 0..3 */);

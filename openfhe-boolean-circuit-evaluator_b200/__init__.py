@@ -19,6 +19,7 @@ TOY, STD128_OPT = 0, 5
 AP, GINX = 0, 1
 OR, AND, NOR, NAND, XOR_FAST, XNOR_FAST, XOR, XNOR, BOOTSTRAP = range(9)
 NEG0, NEG1 = 0x100, 0x200
+OFHE_SECRET_KEY, OFHE_REFRESH_KEY, OFHE_SWITCH_KEY = 0, 1, 2
 ERR_ARG, ERR_STATE, ERR_CUDA, ERR_FORMAT, ERR_ALIAS, ERR_NCCL, ERR_IO = -1, -2, -3, -4, -5, -6, -7
 
 # netlist gate kinds: GateEnum of the reference (src/gate.h:51), then EvalBinGate's other native gate types
@@ -56,6 +57,7 @@ ABI_SYMBOLS = [
     "bfhe_circuit_dump_gate_count", "bfhe_circuit_load_netlist", "bfhe_circuit_get_netlist", "bfhe_circuit_write_out",
     "bfhe_circuit_load_netlist_ex", "bfhe_circuit_set_shard_threshold", "bfhe_circuit_dump_gate_count_ex",
     "bfhe_circuit_dump_text", "bfhe_circuit_dff_plan", "bfhe_circuit_get_schedule",
+    "bfhe_import_openfhe_json", "bfhe_export_openfhe_json", "bfhe_import_openfhe_ct_json", "bfhe_export_openfhe_ct_json",
 ]
 
 _lib = None
@@ -132,6 +134,10 @@ def lib():
     L.bfhe_circuit_dump_text.argtypes = [vp, C.c_int, C.c_char_p, sz, C.POINTER(sz)]
     L.bfhe_circuit_dff_plan.argtypes = [vp, u32p, vp, sz]
     L.bfhe_circuit_get_schedule.argtypes = [vp, u32p, u32p, u32p, C.POINTER(C.c_double)]
+    L.bfhe_import_openfhe_json.argtypes = [vp, C.c_int, C.c_char_p]
+    L.bfhe_export_openfhe_json.argtypes = [vp, C.c_int, C.c_char_p]
+    L.bfhe_import_openfhe_ct_json.argtypes = [vp, C.c_char_p, vp]
+    L.bfhe_export_openfhe_ct_json.argtypes = [vp, vp, C.c_char_p]
     _lib = L
     return L
 
@@ -218,6 +224,22 @@ class Context:
 
     def load_keys(self, path):
         self._ck(self.L.bfhe_load_keys(self.h, path.encode()))
+
+    # OpenFHE 1.0.x cereal JSON objects (row f-3): what = OFHE_SECRET_KEY / OFHE_REFRESH_KEY / OFHE_SWITCH_KEY
+    def import_openfhe_json(self, what, path):
+        self._ck(self.L.bfhe_import_openfhe_json(self.h, what, path.encode()))
+
+    def export_openfhe_json(self, what, path):
+        self._ck(self.L.bfhe_export_openfhe_json(self.h, what, path.encode()))
+
+    def import_openfhe_ct_json(self, path):
+        row = np.zeros(self.stride, dtype=np.uint32)
+        self._ck(self.L.bfhe_import_openfhe_ct_json(self.h, path.encode(), _ptr(row)))
+        return row
+
+    def export_openfhe_ct_json(self, ct_row, path):
+        row = np.ascontiguousarray(ct_row, dtype=np.uint32).reshape(self.stride)
+        self._ck(self.L.bfhe_export_openfhe_ct_json(self.h, _ptr(row), path.encode()))
 
     # host LWE
     def encrypt(self, bits, seed=0):

@@ -37,6 +37,7 @@ struct bfhe_ctx {
   std::vector<bfhe::i32> sk;
   std::vector<bfhe::i32> z; // RLWE key, only between keygen and btkeygen
   bool has_sk = false, has_bt = false;
+  bool ofhe_have_bk = false, ofhe_have_ksk = false; // halves of the bootstrapping key imported from OpenFHE JSON (host/openfhe_json.cpp)
   std::vector<bfhe::u32> bk_coef;
   std::vector<bfhe::u8> ksk; // [N][baseKS][dKS][n+1], ksk_elem_bytes each
   bfhe::u32 ksk_elem_bytes = 4;
