@@ -36,12 +36,16 @@ def build(force=False, verbose=False):
               "-Xcompiler", "-fPIC,-fopenmp,-O3", "-I", os.path.join(HERE, "..", "include")]
     if verbose:
         common += ["-Xptxas", "-v"]
+    jobs = []
     for s in sources():
         o = os.path.join(HERE, "build", os.path.basename(s) + ".o")
         if force or not os.path.exists(o) or any(os.path.getmtime(d) > os.path.getmtime(o) for d in deps()):
-            cmd = common + (["-x", "cu"] if s.endswith(".cpp") else []) + ["-c", s, "-o", o]
-            subprocess.check_call(cmd)
+            jobs.append(common + (["-x", "cu"] if s.endswith(".cpp") else []) + ["-c", s, "-o", o])
         objs.append(o)
+    procs = [subprocess.Popen(cmd) for cmd in jobs]  # one nvcc per translation unit, side by side
+    failed = [p.args for p in procs if p.wait() != 0]
+    if failed:
+        raise subprocess.CalledProcessError(1, failed[0])
     subprocess.check_call([NVCC, "-ccbin", CCBIN, "-shared", "-o", LIB] + objs + ["-lgomp", "-ldl", "-cudart", "static"])
     # C++ example written against the reference-shaped headers (host/circuit.h, host/binfhecontext.h)
     ex = os.path.join(HERE, "examples", "tb_circuit.cpp")

@@ -51,10 +51,9 @@ struct LaunchInfo { // filled by the launch helpers for the profiler hooks
   size_t smem_bytes;
 };
 
-// device buffers of the second-generation throughput kernel (kernels_v2.cu); all null when the parameter set is not covered
+// device buffers of the cluster kernels (kernels_v2.cu, kernels_cl.cu); all null when the parameter set is not covered
 struct V2Bufs {
-  const u32 *d_bk2 = nullptr; // bootstrapping key, rows in the kernel's physical slot order
-  const u32 *d_bk4 = nullptr; // the same, split [step][quarter of the slots][polynomial][N/4]: the 2-CTA and 4-CTA cluster kernels
+  const u32 *d_bk4 = nullptr; // bootstrapping key, rows in kernels_v2.cu's physical slot order, split [step][quarter of the slots][polynomial][N/4]
   const u32 *d_tw2 = nullptr; // fwd w | fwd ws | inv w | inv ws, each N words (order: kernels_v2.cu Tabs)
   const u32 *d_F = nullptr;   // (psi^k - 1) * 2^32 mod Q, k < 2N
   const u32 *d_bkx = nullptr; // slot-sliced 4-CTA cluster kernel (kernels_cl.cu): key as [step][rank][polynomial][N/4]
@@ -62,9 +61,8 @@ struct V2Bufs {
 };
 
 // kernels.cu entry points (all asynchronous on `stream`; return cudaError_t as int)
-// force_gates_per_cta: 0 = cost model; 1, 2, 4 = first-generation throughput form; 8 = latency form; 16 = second-generation
-// throughput form; 32 = cluster latency form (one gate on two SMs); 64 = one gate on four SMs (round-1 form); 128 = one gate on four SMs,
-// slot-sliced (kernels_cl.cu)
+// force_gates_per_cta: 0 = cost model; 1, 2, 4 = throughput form; 8 = latency form; 32 = cluster latency form (one gate on two SMs);
+// 128 = one gate on four SMs, slot-sliced (kernels_cl.cu).  (16 and 64 named two round-1 forms that no longer exist: invalid value.)
 int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates, int count, const u32 *d_bk,
                         const u32 *d_twl /*fwd w | fwd ws | inv w | inv ws, each N words*/, const u32 *d_psiM,
                         u32 *d_ext /*count * (N+4)*/, u32 *d_acc_dbg /*nullable: count*2*N*/, int force_gates_per_cta,
@@ -74,13 +72,7 @@ bool v2_supported(const DevConst &P, int method_ap);
 int v2_set_attrs();
 int launch_bk_permute_v2(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
 int cl2_max_gates(); // gates the cluster form can run concurrently on this device (0 = unavailable)
-int cl4_max_gates();
-int cl4_fast_gates(); // up to this many gates the 4-CTA form beats the 2-CTA form
 int launch_bk_split_cl4(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
-int launch_blind_rotate_cl4(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
-                            void *stream, LaunchInfo *info);
-int launch_blind_rotate_v2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
-                           void *stream, LaunchInfo *info);
 // one gate on a 2-CTA cluster (two SMs): the latency form for wavefronts narrower than half the SM count
 int launch_blind_rotate_cl2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
                             void *stream, LaunchInfo *info);
@@ -88,7 +80,8 @@ int launch_blind_rotate_cl2(const DevConst &P, const DevGate *d_gates, int count
 bool clx_supported(const DevConst &P, int method_ap);
 size_t clx_tw_words();
 int clx_set_attrs();
-int clx_max_gates();
+int clx_max_gates();  // 4-CTA clusters the device keeps co-resident
+int clx_fast_gates(); // up to this many gates the 4-CTA form runs all clusters in one round at full speed
 int launch_bk_slice_clx(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
 int launch_blind_rotate_clx(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
                             void *stream, LaunchInfo *info);

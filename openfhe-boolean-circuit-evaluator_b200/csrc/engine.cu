@@ -227,7 +227,7 @@ extern "C" void bfhe_destroy(bfhe_ctx *c) {
     cudaFree(c->d_bk); cudaFree(c->d_twl); cudaFree(c->d_psiM); cudaFree(c->d_ksk); cudaFree(c->d_gates); cudaFree(c->d_ext);
     cudaFree(c->d_tmp); cudaFree(c->d_ptr_in); cudaFree(c->d_ptr_out); cudaFree(c->e2e_slab);
     cudaFree(c->d_gates_b); cudaFree(c->d_ext_b);
-    cudaFree(c->d_bk2); cudaFree(c->d_bk4); cudaFree(c->d_tw2); cudaFree(c->d_F);
+    cudaFree(c->d_bk4); cudaFree(c->d_tw2); cudaFree(c->d_F);
     cudaFree(c->d_bkx); cudaFree(c->d_twx);
     for (int i = 0; i < 2; i++) {
       if (c->ev_br[i]) cudaEventDestroy(c->ev_br[i]);
@@ -398,17 +398,17 @@ int bfhe::ensure_device_keys(bfhe_ctx *c) {
     }
     cudaFree(d_coef);
   }
-  cudaFree(c->d_bk2); c->d_bk2 = nullptr; c->v2.d_bk2 = nullptr;
   cudaFree(c->d_bk4); c->d_bk4 = nullptr; c->v2.d_bk4 = nullptr;
-  if (c->d_tw2 && v2_supported(c->P, p.method == BFHE_AP)) { // second copy in the physical slot order of kernels_v2.cu
-    BFHE_CUDA(cudaMalloc(&c->d_bk2, c->bk_words * 4));
-    int rc = launch_bk_permute_v2(c->d_bk, c->d_bk2, c->bk_words / N, c->stream);
-    if (rc) return cuda_fail((cudaError_t)rc, "bk_permute_v2");
-    BFHE_CUDA(cudaMalloc(&c->d_bk4, c->bk_words * 4));
-    rc = launch_bk_split_cl4(c->d_bk2, c->d_bk4, c->bk_words / N, c->stream);
-    if (rc) return cuda_fail((cudaError_t)rc, "bk_split_cl4");
-    BFHE_CUDA(cudaStreamSynchronize(c->stream));
-    c->v2.d_bk2 = c->d_bk2;
+  if (c->d_tw2 && v2_supported(c->P, p.method == BFHE_AP)) { // key copy of the 2-CTA cluster kernel: kernels_v2.cu's physical slot order
+    u32 *tmp = nullptr;                                        // (a temporary), split [step][quarter][polynomial][N/4]
+    BFHE_CUDA(cudaMalloc(&tmp, c->bk_words * 4));
+    int rc = launch_bk_permute_v2(c->d_bk, tmp, c->bk_words / N, c->stream);
+    if (rc) { cudaFree(tmp); return cuda_fail((cudaError_t)rc, "bk_permute_v2"); }
+    if (cudaMalloc(&c->d_bk4, c->bk_words * 4) != cudaSuccess) { cudaFree(tmp); return cuda_fail(cudaGetLastError(), "cudaMalloc(d_bk4)"); }
+    rc = launch_bk_split_cl4(tmp, c->d_bk4, c->bk_words / N, c->stream);
+    if (rc) { cudaFree(tmp); return cuda_fail((cudaError_t)rc, "bk_split_cl4"); }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
     c->v2.d_bk4 = c->d_bk4;
   }
   cudaFree(c->d_bkx); c->d_bkx = nullptr; c->v2.d_bkx = nullptr;
@@ -897,7 +897,7 @@ extern "C" int bfhe_dbg_cluster_limits(bfhe_ctx *c, int *cl2_gates, int *cl4_gat
   if (!c || c->device < 0) return BFHE_ERR_ARG;
   BFHE_CUDA(cudaSetDevice(c->device));
   if (cl2_gates) *cl2_gates = cl2_max_gates();
-  if (cl4_gates) *cl4_gates = cl4_max_gates();
+  if (cl4_gates) *cl4_gates = clx_max_gates();
   return BFHE_OK;
 }
 extern "C" int bfhe_dbg_set_gates_per_cta(bfhe_ctx *c, int g) {

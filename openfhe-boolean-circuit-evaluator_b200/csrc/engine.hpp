@@ -46,7 +46,7 @@ struct bfhe_ctx {
   // device key material
   bfhe::u32 *d_bk = nullptr, *d_twl = nullptr, *d_psiM = nullptr;
   void *d_ksk = nullptr;
-  bfhe::u32 *d_bk2 = nullptr, *d_bk4 = nullptr, *d_tw2 = nullptr, *d_F = nullptr; // second-generation throughput kernel (kernels_v2.cu)
+  bfhe::u32 *d_bk4 = nullptr, *d_tw2 = nullptr, *d_F = nullptr; // 2-CTA cluster kernel (kernels_v2.cu)
   bfhe::u32 *d_bkx = nullptr, *d_twx = nullptr; // slot-sliced cluster kernel (kernels_cl.cu)
   bfhe::V2Bufs v2{};
   bool dev_keys = false;

@@ -1215,27 +1215,22 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
                         const u32 *d_psiM, u32 *d_ext, u32 *d_acc_dbg, int force_g, void *stream, LaunchInfo *info, const V2Bufs *v2) {
   if (count <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool have_v2 = v2 && v2->d_bk2 && v2_supported(P, method_ap);
-  if ((force_g == 16 || force_g == 32 || force_g == 64) && !have_v2) return (int)cudaErrorInvalidValue;
+  const bool have_cl2 = v2 && v2->d_bk4 && v2->d_tw2 && v2->d_F && v2_supported(P, method_ap);
   const bool have_clx = v2 && v2->d_bkx && v2->d_twx && v2->d_F && clx_supported(P, method_ap);
   if (force_g == 128) return have_clx ? launch_blind_rotate_clx(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info) : (int)cudaErrorInvalidValue;
-  if (force_g == 32) return launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
-  if (force_g == 64) return launch_blind_rotate_cl4(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
+  if (force_g == 32) return have_cl2 ? launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info) : (int)cudaErrorInvalidValue;
+  if (force_g != 0 && force_g != 1 && force_g != 2 && force_g != 4 && force_g != 8) return (int)cudaErrorInvalidValue;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // Which variant?  latency form: one gate per CTA, one wave of `sms` gates takes ~2.3 ms (STD128_OPT GINX);
-  // throughput form: 4 gates per CTA share every key word, one wave of 4*sms gates takes ~7.6 ms.  Pick the cheaper
-  // estimate (measured on B200, profiles/r1_*): narrow circuit levels go to the latency form, wide batches to the other.
-  // narrower than the number of co-resident 2-CTA clusters: one gate on two SMs (1.49 ms per wave instead of 2.30 ms)
-  if (force_g == 0 && have_v2 && v2->d_bk4 && count <= cl4_fast_gates()) // one gate on four SMs (1.19 - 1.26 ms per wave)
-    return launch_blind_rotate_cl4(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
-  if (force_g == 0 && have_v2 && v2->d_bk4 && count <= cl2_max_gates())
-    return launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
+  // Which variant?  Measured on B200, STD128_OPT GINX (profiles/): one gate on four SMs 1.02 ms per wave of up to 33 gates; one gate on two
+  // SMs 1.49 ms up to 74; latency form (one gate per CTA) 2.3 ms per wave of `sms` gates; throughput form (4 gates per CTA share every
+  // key word) 7.4 ms per wave of 4 * sms gates.  Narrow circuit levels go to the cluster forms, wide batches to the throughput form.
+  if (force_g == 0 && have_clx && count <= clx_fast_gates()) return launch_blind_rotate_clx(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
+  if (force_g == 0 && have_cl2 && count <= cl2_max_gates()) return launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   const long lat_cost = (long)((count + sms - 1) / sms) * 23;
   const long thr_cost = (long)((count + 4 * sms - 1) / (4 * sms)) * 76;
   const bool lat = force_g == 8 || (force_g == 0 && lat_cost <= thr_cost);
-  if (force_g == 16) return launch_blind_rotate_v2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   if (lat) {
     if (P.N == 1024 && P.dG == 4 && P.logBG == 7)
       return method_ap ? launch_lat_inst<10, 4, 7, true>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)
@@ -1245,8 +1240,6 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
                        : launch_lat_inst<9, 3, 9, false>(P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info);
     return (int)cudaErrorInvalidValue;
   }
-  // (the second-generation form, kernels_v2.cu, measures within 1 % of this one -- 76.7k vs 77.5k gates/s in bench.py,
-  //  79.5k vs 79.0k on all-NAND batches -- so the cost model keeps the first-generation kernel; force_g = 16 selects the other)
   int G = force_g > 0 ? force_g : 4;
   if (P.N == 1024 && P.dG == 4 && P.logBG == 7) {
     return method_ap ? launch_br_g<10, 4, 7, true>(G, P, d_gates, count, d_bk, d_twl, d_psiM, d_ext, d_acc_dbg, st, info)

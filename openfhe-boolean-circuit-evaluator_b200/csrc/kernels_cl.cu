@@ -7,17 +7,31 @@
 // (profiles/r1_blind_rotate_cluster4_ncu_summary.md).  This kernel slices everything by evaluation slot instead.  Write the transform of
 // size N as (two stages across the four blocks of N/4 coefficients) o (four independent sub-transforms of size N/4):
 //
-//   * every CTA keeps the WHOLE accumulator (both components, coefficient form, 8 coefficients per thread in registers);
+//   * every CTA keeps the WHOLE accumulator (both components, coefficient form);
 //   * CTA k computes, for all 8 digit polynomials, only block k of the two cross-block stages -- straight from the digits with three
 //     table look-ups per value (digit x {w1, w2, w1 w2} precomputed for the 128 digit values), no multiplication -- and then its own
-//     256-point sub-transform of each (one warp per digit polynomial, 8 values per lane: 3 + 3 register stages, one shared-memory
-//     transpose, 2 stages across lanes by shuffle);
-//   * it multiplies ITS 256 slots of the 8 rows with ITS quarter of the step's key tile (32 KB, TMA bulk copy, double buffered), and
-//     runs the 256-point inverse sub-transform of the two product components (one warp each);
+//     256-point sub-transform of each (one warp per digit polynomial, 8 values per lane: 3 + 3 + 2 register stages, two shared-memory
+//     transposes);
+//   * it multiplies ITS 256 slots of the 8 rows with ITS quarter of the step's key tile (32 KB, TMA bulk copy, double buffered, issued
+//     two steps ahead), and runs the 256-point inverse sub-transform of the two product components;
 //   * the only exchange: the 2 x 256 partial values go to the three peers (st.async, counted on the receiver's mbarrier, 6 KB in and
-//     out per CTA and step); every CTA then finishes the inverse transform redundantly (two cross-block stages, 8 multiplications per
-//     thread), adds to its copy of the accumulator and cuts the next digits.
+//     out per CTA and step); every CTA then finishes the inverse transform redundantly (two cross-block stages), adds to its copy of the
+//     accumulator and cuts the next digits.
 //
+// Third revision (round 2): DSMEM moves ~20 bytes per cycle and SM, so the 6 KB exchange alone is ~300 cycles of a ~4 000-cycle step, and
+// in the second revision every phase was fenced from the next by a CTA barrier.  Here the step is two pipelines, one per accumulator
+// component c, that meet only at the external product:
+//   * warps 4 c .. 4 c + 3 ("group c", 128 threads, one warp per scheduler) own component c: they hold its 1 024 coefficients in registers, run the
+//     cross-block inverse stages for it as soon as ITS partial values have landed (one mbarrier per component and step parity), publish
+//     centred + offset words in shared memory, and -- after a 128-thread named barrier -- each warp cuts its own digit row out of them
+//     (warp 4 c + l transforms row c + 2 l), looks the products up and runs the row's sub-transform straight from registers;
+//   * the product is computed component 0 first: every thread runs the five inverse stages that stay inside its warp (shuffles) and
+//     stores the value into the CTA's own row of the receive buffer; a ninth warp then sends that 1 KB row to the three peers with one
+//     TMA bulk copy each (shared::cta -> shared::cluster, counted on the receiver's mbarrier).  Component 0 is on the wire while the
+//     main warps still multiply component 1, and group 0 is already transforming while component 1 is in flight;
+//   * the three remaining stages of the 256-point inverse sub-transforms run AFTER the exchange, on all four rows at once (warp l of
+//     group c takes the row that came from CTA l), instead of on one warp before it: measured, the single-warp stage plus the hand-off
+//     to it cost ~700 cycles of every step's critical path against ~150 for the redundant arithmetic.
 // No cluster-scope fence or barrier.cluster inside the step loop; receive buffers and their mbarriers alternate by step parity, so a
 // CTA that runs one step ahead cannot overwrite or miscount data its peer is still reading.
 #include "common.hpp"
@@ -26,11 +40,10 @@
 namespace bfhe {
 namespace clx {
 
-constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, NPAD = 512, R = 4, NB = N / R, THREADS = 256;
+constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, NPAD = 512, R = 4, NB = N / R, THREADS = 288; // 8 main warps + the warp that issues the bulk copies
 constexpr int KEYPOLYS = 2 * ROWS * 2;
 constexpr u32 DIGIT_OFF = 64u + (64u << 7) + (64u << 14) + (64u << 21);
 constexpr u32 SOLINAS_Q = (1u << 27) - (1u << 11) + 1;
-constexpr u32 RECV_TX = (u32)(R - 1) * 2 * NB * 4; // bytes the three peers push into a CTA per step
 
 // per-rank twiddle block (host-generated, engine.cu): fw[TWF] | fws[TWF] | iw[TWI] | iws[TWI]
 //   fw:  [0, 8)            pass A (register stages across the 32-strided values), uniform over the warp: w[1], w[2..3], w[4..7]
@@ -65,6 +78,11 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
                "r"(parity)
                : "memory");
 }
+__device__ __forceinline__ bool mbar_test(u64 *bar, u32 parity) { // one try, no loop
+  u32 ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -80,6 +98,16 @@ __device__ __forceinline__ void st_async4(u32 dsmem, uint4 v, u32 dsmem_bar) {
                "r"(v.z), "r"(v.w), "r"(dsmem_bar)
                : "memory");
 }
+
+// local shared memory -> a peer CTA's shared memory, counted on the peer's mbarrier (one TMA bulk copy instead of 64 st.async)
+__device__ __forceinline__ void bulk_s2peer(u32 dsmem_dst, const void *src, u32 bytes, u32 dsmem_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dsmem_dst), "r"(smem_u32(src)), "r"(bytes),
+               "r"(dsmem_bar)
+               : "memory");
+}
+#ifndef CLX_ISSUE_PAR
+#define CLX_ISSUE_PAR 0 // 1: the three bulk copies of a row are issued by three lanes instead of one after the other (measured: slower, 1.075 vs 1.02 ms)
+#endif
 
 // ---- 8-value register stages.  Stage with half-size T pairs a = g * 2T + (i % T), b = a + T and uses twiddle w[8 / (2T) + g] ----
 template <int T> __device__ __forceinline__ void ct8_stage(u32 (&x)[8], const u32 (&w)[8], const u32 (&ws)[8], u32 Q, u32 Q2) {
@@ -141,24 +169,36 @@ __host__ __device__ __forceinline__ int slot_position(int k, int t) { return NB 
 
 struct Smem { // word offsets
   static constexpr int rbuf = 0;                              // [parity 2][source CTA R][component 2][NB]
-  static constexpr int dct = rbuf + 2 * R * 2 * NB;           // [ROWS][NB]
-  static constexpr int prod = dct + ROWS * NB;                // [2][NB]
-  static constexpr int lut = prod + 2 * NB;                   // [3][128][32]
+  static constexpr int dct = rbuf + 2 * R * 2 * NB;           // [parity 2][ROWS][NB]
+  static constexpr int pbuf = dct + 2 * ROWS * NB;            // [component 2][source CTA R][NB] rows after the last sub-transform stages
+  static constexpr int accs = pbuf + 2 * R * NB;              // [2][N] centred accumulator + digit offset
+  static constexpr int lut = accs + 2 * N;                    // [3][128][32]
   static constexpr int F = lut + 3 * 128 * 32;                // [2N]
-  static constexpr int idx = F + 2 * N;                       // u16 [NPAD]
-  static constexpr int bars = idx + NPAD / 2;                 // rbar[2]
-  static constexpr int words = bars + 4;
+  static constexpr int key = F + 2 * N;                       // [parity 2][8 quads][NB][4]
+  static constexpr int idx = key + 2 * KEYPOLYS * NB;         // u16 [NPAD]
+  static constexpr int bars = idx + NPAD / 2;                 // rbar[parity 2][component 2], kbar[2]
+  static constexpr int words = bars + 12;
   static constexpr size_t bytes = (size_t)words * 4;
 };
+static_assert(Smem::key % 32 == 0 && Smem::bars % 2 == 0, "TMA destination 128-byte aligned, mbarriers 8-byte aligned");
+constexpr u32 KEYBYTES = KEYPOLYS * NB * 4;     // this CTA's quarter of one step's key tile
+constexpr u32 RECV_TX_C = (u32)(R - 1) * NB * 4; // bytes the three peers push into a CTA per step and component
+
+// named barriers (0 is left to __syncthreads in the prologue)
+constexpr int BAR_DCT = 1, BAR_GROUP = 2 /* + c */, BAR_PROD = 4 /* + c */;
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 __global__ void __cluster_dims__(R, 1, 1) __launch_bounds__(THREADS, 1)
 blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count, const u32 *__restrict__ bkx,
                         const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   u32 *sm = reinterpret_cast<u32 *>(smem_raw);
-  u32 *rbuf = sm + Smem::rbuf, *dct = sm + Smem::dct, *prod = sm + Smem::prod, *s_lut = sm + Smem::lut, *s_F = sm + Smem::F;
+  u32 *rbuf = sm + Smem::rbuf, *dct = sm + Smem::dct, *pbuf = sm + Smem::pbuf, *accs = sm + Smem::accs, *s_lut = sm + Smem::lut, *s_F = sm + Smem::F,
+      *s_key = sm + Smem::key;
   u16 *s_idx = reinterpret_cast<u16 *>(sm + Smem::idx);
-  u64 *rbar = reinterpret_cast<u64 *>(sm + Smem::bars);
+  u64 *rbar = reinterpret_cast<u64 *>(sm + Smem::bars); // [parity][component]
+  u64 *kbar = rbar + 4;
   __shared__ u32 s_b;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -168,7 +208,8 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   const DevGate dg = gates[gi];
 
   if (tid == 0) {
-    mbar_init(rbar + 0, 1); mbar_init(rbar + 1, 1);
+    for (int i = 0; i < 4; i++) mbar_init(rbar + i, 1);
+    mbar_init(kbar + 0, 1); mbar_init(kbar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 2 * N; i += THREADS) s_F[i] = g_F[i];
@@ -207,88 +248,145 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   }
   __syncthreads();
 
-  // accumulator: thread t holds coefficients t + 256 i1 (i1 = 0..3) of both components, canonical [0, Q)
+  auto issue_keys = [&](u32 step) { // one thread: this CTA's 32 KB of step `step`, [step][rank][quad][slot][4] contiguous
+    u64 *bar = kbar + (step & 1);
+    mbar_expect_tx(bar, KEYBYTES);
+    const u32 *src = bkx + ((size_t)step * R + k) * KEYPOLYS * NB;
+    u32 *dst = s_key + (size_t)(step & 1) * KEYPOLYS * NB;
+    bulk_g2s(dst, src, 16384, bar);
+    bulk_g2s(dst + 4096, src + 4096, 16384, bar);
+  };
+  static_assert(KEYBYTES == 2 * 16384, "two bulk copies");
+
+  const u32 *twr = g_tw + (size_t)k * TWR, *g_fw = twr, *g_fws = twr + TWF, *g_iw = twr + 2 * TWF, *g_iws = twr + 2 * TWF + TWI;
+#ifdef BFHE_PHASE_TIMING
+  long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tc0 = clock64(), tc1;
+  u32 tstamp[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tstep = 0; // absolute clock (low 32 bits) of every mark in step 200: one step's timeline
+#define CLX_T(i) do { tc1 = clock64(); tph[i] += tc1 - tc0; tc0 = tc1; if (tstep == 200) tstamp[i] = (u32)tc1; } while (0)
+#else
+#define CLX_T(i)
+#endif
+
+  if (warp >= 8) {
+    // ================= issue warp: sends this CTA's finished rows to the peers and fetches the key tiles =================
+    if (lane == (CLX_ISSUE_PAR ? R : 0) && n > 0) {
+      issue_keys(0);
+      if (n > 1) issue_keys(1);
+    }
+    // shared::cluster addresses in "my" peer (lane p < 3 serves peer (k + 1 + p) % R): receive buffer, rbar[0][0]
+    const u32 my_dest = (k + 1 + (u32)(lane < R - 1 ? lane : 0)) % R;
+    const u32 my_peer_rbuf = dsmem_addr(rbuf, my_dest), my_peer_bar = dsmem_addr(rbar, my_dest);
+    cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
+    for (u32 step = 0; step < n; step++) {
+      const u32 par = step & 1;
+#ifdef BFHE_PHASE_TIMING
+      tstep = step;
+#endif
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        bar_sync(BAR_PROD + c, 256 + 32); // all 256 product threads have stored component c (and, for c = 1, are done with the key tile)
+        CLX_T(2 * c);
+        const u32 roww = (u32)(((par * R + k) * 2 + c) * NB);
+#if CLX_ISSUE_PAR
+        if (lane < R - 1) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the writers' generic-proxy stores (ordered before me by the barrier), before the async proxy reads them
+          bulk_s2peer(my_peer_rbuf + roww * 4u, rbuf + roww, NB * 4, my_peer_bar + 16u * par + 8u * c); // lane p -> peer (k + 1 + p) % R
+        } else if (lane == R - 1) {
+          // one arrival per step and component: it releases the CTA's own row to group c and posts the bytes expected from the three
+          // peers (copies that landed earlier merely ran the count negative)
+          mbar_expect_tx(rbar + par * 2 + c, RECV_TX_C);
+        } else if (lane == R && c == 1 && step + 2 < n) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the product's reads of this key buffer, before the async proxy overwrites it
+          issue_keys(step + 2);
+        }
+#else
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the writers' generic-proxy stores (ordered before me by the barrier), before the async proxy reads them
+#pragma unroll
+          for (int p = 0; p < R - 1; p++)
+            bulk_s2peer(dsmem_addr(rbuf + roww, (k + 1 + p) % R), rbuf + roww, NB * 4, dsmem_addr(rbar + par * 2 + c, (k + 1 + p) % R));
+          mbar_expect_tx(rbar + par * 2 + c, RECV_TX_C); // one arrival per step and component (see the other branch)
+          if (c == 1 && step + 2 < n) issue_keys(step + 2);
+        }
+#endif
+        CLX_T(2 * c + 1);
+      }
+    }
+    cluster_sync_all(); // a CTA must not exit while its peers may still push into its shared memory
+#ifdef BFHE_PHASE_TIMING
+    if (acc_dbg && lane == 0) // after the main warps' accumulator dump (they reach the cluster barrier after it)
+      for (int i = 0; i < 10; i++) {
+        acc_dbg[(gi * 2 + 1) * N + NB * k + 32 + 16 * 2 + i] = (u32)(tph[i] / 1000); // kilo-cycles
+        acc_dbg[(gi * 2 + 0) * N + NB * k + 32 + 16 * 2 + i] = tstamp[i];
+      }
+#endif
+    return;
+  }
+
+  // ================= main warps: warp 4 c + l transforms row c + 2 l; group c = warps 4 c .. 4 c + 3, one per scheduler =================
+  const int c = warp >> 2, l = warp & 3, gt = l * 32 + lane; // gt: index inside the group, 0..127
+  // accumulator: group c, thread gt holds coefficients gt + 128 jj + 256 i1 of component c, canonical [0, Q)
   u32 acc[2][4];
   {
     const u32 gate = dg.op & 0xff;
     const u32 q1 = P.gate_const[gate == OP_BOOTSTRAP ? OP_AND : gate], q2 = (q1 + q / 2) % q, b = s_b;
 #pragma unroll
-    for (int i1 = 0; i1 < 4; i1++) {
-      acc[0][i1] = 0;
-      const u32 idx = tid + NB * i1;
-      u32 v = 0;
-      if (idx % P.factor == 0) {
-        const u32 t = (b + q - idx / P.factor) % q;
-        const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
-        v = in ? Q - P.Q8 : P.Q8;
+    for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+      for (int i1 = 0; i1 < 4; i1++) {
+        const u32 idx = gt + 128 * jj + NB * i1;
+        u32 v = 0;
+        if (c == 1 && idx % P.factor == 0) {
+          const u32 t = (b + q - idx / P.factor) % q;
+          const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
+          v = in ? Q - P.Q8 : P.Q8;
+        }
+        acc[jj][i1] = v;
+        accs[c * N + idx] = ((v < (Q >> 1)) ? v : v - Q) + DIGIT_OFF; // centred + offset
       }
-      acc[1][i1] = v;
-    }
   }
-  cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
-
   // ---- per-thread constants, kept in registers for the whole blind rotation ----
   const u32 ex = 2 * (__brev((u32)slot_position((int)k, tid)) >> (32 - LOGN)) + 1; // MAC slot tid evaluates at psi^ex
-  const u32 *twr = g_tw + (size_t)k * TWR, *g_fw = twr, *g_fws = twr + TWF, *g_iw = twr + 2 * TWF, *g_iws = twr + 2 * TWF + TWI;
-  u32 fA[8], fAs[8], fB[8], fBs[8], fC[8], fCs[8], iA[8], iAs[8], iS[5], iSs[5];
+  u32 fA[8], fAs[8], fB[8], fBs[8], fC[8], fCs[8], iS[5], iSs[5];
 #pragma unroll
-  for (int p = 0; p < 8; p++) { fA[p] = g_fw[p]; fAs[p] = g_fws[p]; iA[p] = g_iw[p]; iAs[p] = g_iws[p]; }
+  for (int p = 0; p < 8; p++) { fA[p] = g_fw[p]; fAs[p] = g_fws[p]; }
   load8(g_fw + 8, fB, lane); load8(g_fws + 8, fBs, lane);
   load8(g_fw + 8 + 256, fC, lane); load8(g_fws + 8 + 256, fCs, lane);
 #pragma unroll
   for (int s5 = 0; s5 < 5; s5++) { iS[s5] = g_iw[8 + 256 * s5 + tid]; iSs[s5] = g_iws[8 + 256 * s5 + tid]; }
   const u32 iw1 = P.itw[1], iw1s = P.itws[1], iwb = P.itw[2], iwbs = P.itws[2], iwc = P.itw[3], iwcs = P.itws[3];
-  const int blk = lane >> 2, qq = lane & 3;
-  u32 peer_rbuf[R - 1], peer_bar[R - 1]; // shared::cluster addresses in the three peers (receive buffer, rbar[0]; rbar[1] is 8 bytes on)
+  u32 iA[8], iAs[8]; // last three stages of the inverse sub-transform of block l (the row that CTA l sends)
 #pragma unroll
-  for (int p = 0; p < R - 1; p++) {
-    const u32 dest = (k + 1 + p) % R;
-    peer_rbuf[p] = dsmem_addr(rbuf, dest);
-    peer_bar[p] = dsmem_addr(rbar, dest);
-  }
-  // this CTA's quarter of the key, word `tid` of each of the 32 polynomials of a step: [step][rank][polynomial][NB]
-  const u32 *kbase = bkx + (size_t)k * KEYPOLYS * NB + tid;
+  for (int p = 0; p < 8; p++) { iA[p] = g_tw[(size_t)l * TWR + 2 * TWF + p]; iAs[p] = g_tw[(size_t)l * TWR + 2 * TWF + TWI + p]; }
+  const int blk = lane >> 2, qq = lane & 3;
+  const u32 dsh = (u32)(LOGBG * l); // my row's digit
+  cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
 
-#ifdef BFHE_PHASE_TIMING
-  long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tc0 = clock64(), tc1;
-#define CLX_T(i) do { tc1 = clock64(); tph[i] += tc1 - tc0; tc0 = tc1; } while (0)
-#else
-#define CLX_T(i)
-#endif
   for (u32 step = 0; step < n; step++) {
     const u32 par = step & 1;
-    if (tid == 0) mbar_expect_tx(rbar + par, RECV_TX); // this step's receive expectation (early pushes merely run the count negative)
-    // the step's key words go straight from L2 into registers; the loads are in flight during phases A and B (no staging buffer, no
-    // mbarrier: the round-1 cluster kernels spent ~200-400 cycles per step issuing and waiting for their TMA key tile)
-    u32 kreg[KEYPOLYS];
-    {
-      const u32 *kp = kbase + (size_t)step * R * KEYPOLYS * NB;
-#pragma unroll
-      for (int pl = 0; pl < KEYPOLYS; pl++) kreg[pl] = __ldg(kp + pl * NB);
-    }
-    // ---- phase A: digits of the accumulator -> block k of the two cross-block forward stages, by table look-up ----
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-      u32 dp[4];
-#pragma unroll
-      for (int i1 = 0; i1 < 4; i1++) dp[i1] = ((acc[c][i1] < (Q >> 1)) ? acc[c][i1] : acc[c][i1] - Q) + DIGIT_OFF; // centred + offset
-#pragma unroll
-      for (int l = 0; l < DG; l++) {
-        const u32 d0 = (dp[0] >> (LOGBG * l)) & 127u, d1 = (dp[1] >> (LOGBG * l)) & 127u, d2 = (dp[2] >> (LOGBG * l)) & 127u,
-                  d3 = (dp[3] >> (LOGBG * l)) & 127u;
-        const u32 y = (d0 + (Q - 64u)) + s_lut[((0 * 128 + d2) << 5) + lane] + s_lut[((1 * 128 + d1) << 5) + lane] + s_lut[((2 * 128 + d3) << 5) + lane];
-        dct[(c + 2 * l) * NB + rowpos(tid)] = y; // lazy, < 4Q + 64
-      }
-    }
+#ifdef BFHE_PHASE_TIMING
+    tstep = step;
+#endif
+    // the key tile of this step was requested two steps ago: test its barrier once now (the ~100 cycles of a try_wait then overlap the
+    // transform); the monomial factors do not depend on the transform either
+    const bool key_in = mbar_test(kbar + par, (step >> 1) & 1);
+    const u32 mono = s_idx[step] * ex;
+    const u32 fp = s_F[f_index(mono)], fn = s_F[f_index(0u - mono)]; // (X^m - 1), (X^-m - 1) at this slot, Montgomery form
+    // ---- phase A: my group's accumulator words are published -> block k of the two cross-block forward stages of MY row, by look-up ----
+    bar_sync(BAR_GROUP + c, 128);
     CLX_T(0);
-    __syncthreads();
-    CLX_T(1);
-    // ---- phase B: warp w transforms row w (256 points, 8 per lane): 3 + 3 + 2 register stages, two in-place transposes ----
+    u32 *row = dct + (par * ROWS + c + 2 * l) * NB;
     {
-      u32 *row = dct + warp * NB;
       u32 x[8];
+      const u32 *ap = accs + c * N + lane;
 #pragma unroll
-      for (int m = 0; m < 8; m++) x[m] = row[rowpos(lane + 32 * m)];
+      for (int m = 0; m < 8; m++) {
+        const u32 d0 = (ap[32 * m] >> dsh) & 127u, d1 = (ap[32 * m + NB] >> dsh) & 127u, d2 = (ap[32 * m + 2 * NB] >> dsh) & 127u,
+                  d3 = (ap[32 * m + 3 * NB] >> dsh) & 127u;
+        x[m] = (d0 + (Q - 64u)) + s_lut[((0 * 128 + d2) << 5) + lane] + s_lut[((1 * 128 + d1) << 5) + lane] + s_lut[((2 * 128 + d3) << 5) + lane]; // < 4Q + 64
+      }
+      CLX_T(1);
+      // ---- phase B: the row's 256-point sub-transform, 8 values per lane: 3 + 3 + 2 register stages, two in-place transposes ----
       ct8_stage<4>(x, fA, fAs, Q, Q2); ct8_stage<2>(x, fA, fAs, Q, Q2); ct8_stage<1>(x, fA, fAs, Q, Q2);
 #pragma unroll
       for (int m = 0; m < 8; m++) row[rowpos(lane + 32 * m)] = x[m];
@@ -309,112 +407,153 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
       *reinterpret_cast<uint4 *>(row + 8 * lane + 4) = make_uint4(x[4], x[5], x[6], x[7]);
     }
     CLX_T(2);
-    __syncthreads();
+    bar_sync(BAR_DCT, 256); // all eight rows of this step are in dct[par]
     CLX_T(3);
-    // ---- phase C: external product on my 256 slots, one slot per thread, then the five inverse stages that stay inside a warp ----
+    // ---- phase C: external product on my 256 slots, one slot per thread, component 0 first; the five inverse stages that stay inside a warp
+    //      (component 0's are independent of component 1's multiplications: the scheduler overlaps them); every finished value goes
+    //      straight into this CTA's row of the receive buffer ----
+    if (!key_in) mbar_wait(kbar + par, (step >> 1) & 1);
+    CLX_T(4);
     {
-      const u32 m = s_idx[step];
-      const u32 y = m * ex, ny = 0u - y;
-      const u32 fp = s_F[f_index(y)], fn = s_F[f_index(ny)]; // (X^m - 1), (X^-m - 1) at this slot, Montgomery form
-      u64 sp[2] = {0, 0}, sn[2] = {0, 0};
+      u32 d[ROWS];
 #pragma unroll
-      for (int rw = 0; rw < ROWS; rw++) {
-        const u32 d = dct[rw * NB + tid];
+      for (int rw = 0; rw < ROWS; rw++) d[rw] = dct[(par * ROWS + rw) * NB + tid];
+      const uint4 *k4 = reinterpret_cast<const uint4 *>(s_key + (size_t)par * KEYPOLYS * NB) + tid; // quad g = (cc * 2 + sign) * 2 + half
+      u32 *mine = rbuf + (size_t)((par * R + k) * 2) * NB + tid;
+      auto mac = [&](int cc) -> u32 {
+        u64 s2[2] = {0, 0};
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-          sp[cc] += (u64)d * kreg[(0 * ROWS + rw) * 2 + cc];
-          sn[cc] += (u64)d * kreg[(1 * ROWS + rw) * 2 + cc];
-        }
-      }
-      CLX_T(4);
+        for (int sg = 0; sg < 2; sg++)
 #pragma unroll
-      for (int cc = 0; cc < 2; cc++) {
-        u32 v = redc((u64)redc(sp[cc], Q, qinv) * fp + (u64)redc(sn[cc], Q, qinv) * fn, Q, qinv); // < 2Q
-        using T0 = GsShfl1<2>; using T1 = GsShfl1<T0::OUTB>; using T2 = GsShfl1<T1::OUTB>; using T3 = GsShfl1<T2::OUTB>; using T4 = GsShfl1<T3::OUTB>;
-        v = T0::run(v, iS[0], iSs[0], Q, 1, (lane & 1) != 0);
-        v = T1::run(v, iS[1], iSs[1], Q, 2, (lane & 2) != 0);
-        v = T2::run(v, iS[2], iSs[2], Q, 4, (lane & 4) != 0);
-        v = T3::run(v, iS[3], iSs[3], Q, 8, (lane & 8) != 0);
-        v = T4::run(v, iS[4], iSs[4], Q, 16, (lane & 16) != 0);
-        static_assert(T4::OUTB == 4, "bound of the values handed to the last three inverse stages");
-        prod[cc * NB + tid] = v;
-      }
+          for (int hf = 0; hf < 2; hf++) {
+            const uint4 kv = k4[((cc * 2 + sg) * 2 + hf) * NB];
+            s2[sg] += (u64)d[4 * hf + 0] * kv.x;
+            s2[sg] += (u64)d[4 * hf + 1] * kv.y;
+            s2[sg] += (u64)d[4 * hf + 2] * kv.z;
+            s2[sg] += (u64)d[4 * hf + 3] * kv.w;
+          }
+        return redc((u64)redc(s2[0], Q, qinv) * fp + (u64)redc(s2[1], Q, qinv) * fn, Q, qinv); // < 2Q
+      };
+      using T0 = GsShfl1<2>; using T1 = GsShfl1<T0::OUTB>; using T2 = GsShfl1<T1::OUTB>; using T3 = GsShfl1<T2::OUTB>; using T4 = GsShfl1<T3::OUTB>;
+      static_assert(T4::OUTB == 4, "bound of the values handed to the last three inverse stages");
+      auto tail = [&](u32 t) -> u32 {
+        t = T0::run(t, iS[0], iSs[0], Q, 1, (lane & 1) != 0);
+        t = T1::run(t, iS[1], iSs[1], Q, 2, (lane & 2) != 0);
+        t = T2::run(t, iS[2], iSs[2], Q, 4, (lane & 4) != 0);
+        t = T3::run(t, iS[3], iSs[3], Q, 8, (lane & 8) != 0);
+        return T4::run(t, iS[4], iSs[4], Q, 16, (lane & 16) != 0);
+      };
+      u32 t0 = mac(0);
+      // component 0's shuffle stages, each followed by a quarter of component 1's multiplications (independent work in the shadow of the
+      // shuffle latency)
+      u64 s1[2] = {0, 0};
+      auto mac1_quarter = [&](int sg, int hf) {
+        const uint4 kv = k4[((1 * 2 + sg) * 2 + hf) * NB];
+        s1[sg] += (u64)d[4 * hf + 0] * kv.x;
+        s1[sg] += (u64)d[4 * hf + 1] * kv.y;
+        s1[sg] += (u64)d[4 * hf + 2] * kv.z;
+        s1[sg] += (u64)d[4 * hf + 3] * kv.w;
+      };
+      t0 = T0::run(t0, iS[0], iSs[0], Q, 1, (lane & 1) != 0);
+      mac1_quarter(0, 0);
+      t0 = T1::run(t0, iS[1], iSs[1], Q, 2, (lane & 2) != 0);
+      mac1_quarter(0, 1);
+      t0 = T2::run(t0, iS[2], iSs[2], Q, 4, (lane & 4) != 0);
+      mac1_quarter(1, 0);
+      t0 = T3::run(t0, iS[3], iSs[3], Q, 8, (lane & 8) != 0);
+      mac1_quarter(1, 1);
+      t0 = T4::run(t0, iS[4], iSs[4], Q, 16, (lane & 16) != 0);
+      mine[0] = t0;
+      bar_arrive(BAR_PROD + 0, 256 + 32); // the issue warp takes over
+      CLX_T(5);
+      const u32 v1 = redc((u64)redc(s1[0], Q, qinv) * fp + (u64)redc(s1[1], Q, qinv) * fn, Q, qinv); // < 2Q
+      mine[NB] = tail(v1);
+      bar_arrive(BAR_PROD + 1, 256 + 32);
     }
-    CLX_T(5);
-    __syncthreads();
     CLX_T(6);
-    // ---- phase D: warps 0 / 1: the last three inverse stages of product component 0 / 1; push the partial values to the peers ----
-    if (warp < 2) {
+    // ---- phase E: my component's four partial rows have landed (mine stored above, the peers' by bulk copy).  Warp l of the group runs the
+    //      last three stages of the inverse sub-transform on the row that came from CTA l; then, across the rows, the two cross-block
+    //      stages for coefficients gt + 128 jj + 256 i1; accumulate; publish centred + offset ----
+    mbar_wait(rbar + par * 2 + c, (step >> 1) & 1);
+    CLX_T(7);
+    {
+      // (not in place: this CTA's own row is still the source of bulk copies that may be in flight)
+      const u32 *rrow = rbuf + (size_t)((par * R + l) * 2 + c) * NB + lane;
+      u32 *prow = pbuf + (size_t)(c * R + l) * NB + lane;
       u32 x[8];
-      const u32 *pr = prod + warp * NB;
 #pragma unroll
-      for (int m = 0; m < 8; m++) x[m] = pr[lane + 32 * m];
+      for (int m = 0; m < 8; m++) x[m] = rrow[32 * m];
       using S2 = Gs8<1, 4>; using S1 = Gs8<2, S2::OUTB>; using S0 = Gs8<4, S1::OUTB>;
       S2::run(x, iA, iAs, Q); S1::run(x, iA, iAs, Q); S0::run(x, iA, iAs, Q);
       static_assert(S0::OUTB <= 4, "partial values must stay below 4Q for the cross-block stages");
-      // my own copy, natural order j = lane + 32 m; then 16-byte pushes of 4 consecutive j to the three peers
-      u32 *mine = rbuf + ((par * R + k) * 2 + warp) * NB;
 #pragma unroll
-      for (int m = 0; m < 8; m++) mine[lane + 32 * m] = x[m];
-      __syncwarp();
-      const uint4 v0 = *reinterpret_cast<const uint4 *>(mine + 4 * lane), v1 = *reinterpret_cast<const uint4 *>(mine + 128 + 4 * lane);
-      const u32 off = (u32)(((par * R + k) * 2 + warp) * NB + 4 * lane) * 4u;
-#pragma unroll
-      for (int p = 0; p < R - 1; p++) {
-        st_async4(peer_rbuf[p] + off, v0, peer_bar[p] + 8u * par);
-        st_async4(peer_rbuf[p] + off + 512u, v1, peer_bar[p] + 8u * par);
-      }
+      for (int m = 0; m < 8; m++) prow[32 * m] = x[m];
     }
-    CLX_T(7);
-    __syncthreads(); // my own partial values are visible to all my warps
-    mbar_wait(rbar + par, (step >> 1) & 1); // ... and the peers' have landed
-    CLX_T(8);
-    // ---- phase E: the two cross-block inverse stages for coefficients tid + 256 i1, both components; accumulate ----
+    bar_sync(BAR_GROUP + c, 128);
+    CLX_T(9);
 #pragma unroll
-    for (int c = 0; c < 2; c++) {
-      const u32 *rb = rbuf + (size_t)(par * R) * 2 * NB + c * NB + tid;
-      const u32 p0 = rb[0 * 2 * NB], p1 = rb[1 * 2 * NB], p2 = rb[2 * 2 * NB], p3 = rb[3 * 2 * NB]; // partial values of blocks 0..3, < 4Q
+    for (int jj = 0; jj < 2; jj++) {
+      const u32 *rb = pbuf + (size_t)c * R * NB + gt + 128 * jj;
+      const u32 p0 = rb[0 * NB], p1 = rb[1 * NB], p2 = rb[2 * NB], p3 = rb[3 * NB]; // partial values of blocks 0..3, < 4Q
       const u32 u0 = p0 + p1, u1 = mul_shoup(p0 - p1 + 4 * Q, iwb, iwbs, Q);
       const u32 u2 = p2 + p3, u3 = mul_shoup(p2 - p3 + 4 * Q, iwc, iwcs, Q);
       const u32 x0 = u0 + u2, x2 = mul_shoup(u0 - u2 + 8 * Q, iw1, iw1s, Q); // u0, u2 < 8Q
       const u32 x1 = u1 + u3, x3 = mul_shoup(u1 - u3 + 2 * Q, iw1, iw1s, Q); // u1, u3 < 2Q
-      acc[c][0] = csub(acc[c][0] + csub(lazy_reduce(x0, Q), Q), Q);
-      acc[c][1] = csub(acc[c][1] + csub(lazy_reduce(x1, Q), Q), Q);
-      acc[c][2] = csub(acc[c][2] + csub(x2, Q), Q);
-      acc[c][3] = csub(acc[c][3] + csub(x3, Q), Q);
+      acc[jj][0] = csub(acc[jj][0] + csub(lazy_reduce(x0, Q), Q), Q);
+      acc[jj][1] = csub(acc[jj][1] + csub(lazy_reduce(x1, Q), Q), Q);
+      acc[jj][2] = csub(acc[jj][2] + csub(x2, Q), Q);
+      acc[jj][3] = csub(acc[jj][3] + csub(x3, Q), Q);
+#pragma unroll
+      for (int i1 = 0; i1 < 4; i1++) {
+        const u32 a = acc[jj][i1];
+        accs[c * N + gt + 128 * jj + NB * i1] = ((a < (Q >> 1)) ? a : a - Q) + DIGIT_OFF;
+      }
     }
-    CLX_T(9);
+    CLX_T(8);
   }
 
-  // ---- epilogue: sample extraction (a14) and ModSwitch Q -> qKS (a15); CTA k writes the coefficients tid + 256 k ----
+  // ---- epilogue: sample extraction (a14) and ModSwitch Q -> qKS (a15); CTA k writes the coefficients of block k ----
   {
     u32 *e = ext + gi * (N + 4);
     const u64 qKS = P.qKS;
     auto modswitch = [&](u32 v) -> u32 { return (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS); };
 #pragma unroll
-    for (int i1 = 0; i1 < 4; i1++) {
-      if ((u32)i1 != k) continue;
-      const u32 j = tid + NB * i1;
-      if (acc_dbg) { acc_dbg[(gi * 2 + 0) * N + j] = acc[0][i1]; acc_dbg[(gi * 2 + 1) * N + j] = acc[1][i1]; }
-      const u32 a = acc[0][i1];
-      const u32 v = (j == 0) ? a : (a == 0 ? 0 : Q - a); // Transpose: a'_0 = a_0, a'_k = -a_{N-k}
-      e[(j == 0) ? 0 : N - j] = modswitch(v);
-      if (j == 0) e[N] = modswitch(csub(acc[1][i1] + P.Q8, Q));
-    }
+    for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+      for (int i1 = 0; i1 < 4; i1++) {
+        if ((u32)i1 != k) continue;
+        const u32 j = gt + 128 * jj + NB * i1;
+        if (acc_dbg) acc_dbg[(gi * 2 + c) * N + j] = acc[jj][i1];
+        if (c == 0) {
+          const u32 a = acc[jj][i1];
+          const u32 v = (j == 0) ? a : (a == 0 ? 0 : Q - a); // Transpose: a'_0 = a_0, a'_k = -a_{N-k}
+          e[(j == 0) ? 0 : N - j] = modswitch(v);
+        } else if (j == 0) {
+          e[N] = modswitch(csub(acc[jj][i1] + P.Q8, Q));
+        }
+      }
   }
 #ifdef BFHE_PHASE_TIMING
-  if (acc_dbg && lane == 0 && (warp == 0 || warp == 7))
-    for (int i = 0; i < 10; i++) acc_dbg[(gi * 2 + 1) * N + NB * k + 32 + 16 * (warp == 7) + i] = (u32)(tph[i] / 1000); // kilo-cycles
+  __syncwarp();
+  bar_sync(BAR_DCT, 256); // the accumulator dump above is complete before the counters overwrite part of it
+  if (acc_dbg && lane == 0 && (warp == 0 || warp == 4))
+    for (int i = 0; i < 10; i++) {
+      acc_dbg[(gi * 2 + 1) * N + NB * k + 32 + 16 * c + i] = (u32)(tph[i] / 1000); // kilo-cycles
+      acc_dbg[(gi * 2 + 0) * N + NB * k + 32 + 16 * c + i] = tstamp[i];
+    }
 #endif
   cluster_sync_all(); // a CTA must not exit while its peers may still push into its shared memory
 }
 
-// key copy of this kernel: [step][rank][polynomial][slot t] <- evaluation-form key of kernels.cu ([chunk][lane][4] word order, slot P =
-// 32 lane + 4 chunk + r holds the evaluation at psi^(2 bitrev(P) + 1))
+// key copy of this kernel: [step][rank][quad g][slot t][4] <- evaluation-form key of kernels.cu ([chunk][lane][4] word order, slot P =
+// 32 lane + 4 chunk + r holds the evaluation at psi^(2 bitrev(P) + 1)).  Quad g = (cc * 2 + sign) * 2 + half holds rows 4 half .. 4 half + 3
+// of output component cc and key sign: one LDS.128 per quad in the product, and component 0's half of the tile is read first.
 __global__ void bk_slice_clx_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t nsteps) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsteps * KEYPOLYS * N; i += (size_t)gridDim.x * blockDim.x) {
     const size_t step = i / ((size_t)KEYPOLYS * N), rem = i % ((size_t)KEYPOLYS * N);
-    const int rk = (int)(rem / ((size_t)KEYPOLYS * NB)), pl = (int)((rem / NB) % KEYPOLYS), t = (int)(rem % NB);
+    const int rk = (int)(rem / ((size_t)KEYPOLYS * NB)), g = (int)((rem / (NB * 4)) % 8), t = (int)((rem / 4) % NB), e = (int)(rem % 4);
+    const int cc = g >> 2, sg = (g >> 1) & 1, hf = g & 1, rw = 4 * hf + e;
+    const int pl = (sg * ROWS + rw) * 2 + cc; // polynomial index of kernels.cu's key: [sign][row][column]
     const int Ppos = slot_position(rk, t), sl = Ppos >> 5, j = Ppos & 31;
     dst[i] = src[(step * KEYPOLYS + pl) * N + ((j >> 2) * 32 + sl) * 4 + (j & 3)];
   }
@@ -469,6 +608,9 @@ int clx_max_gates() { // 4-CTA clusters of this kernel the device keeps co-resid
   }
   return cached[d];
 }
+// The occupancy query is exact for this kernel (B200: 33 clusters; measured 1.02 ms per wave up to 33 gates, 2.03 ms -- a second round --
+// from 34 on), so the whole co-resident maximum runs at full speed.
+int clx_fast_gates() { return clx_max_gates(); }
 int launch_bk_slice_clx(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
   if (npoly == 0) return 0;
   clx::bk_slice_clx_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly / clx::KEYPOLYS);

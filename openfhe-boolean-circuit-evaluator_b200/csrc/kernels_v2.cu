@@ -1,24 +1,14 @@
-// kernels_v2.cu -- the GINX blind rotation on 16-value / 8-value register tiles (STD128_OPT shape: N = 1024, dG = 4, Bg = 2^7):
-//   blind_rotate_v2_kernel   four gates per CTA, 16 warps (throughput form, measured equal to kernels.cu's; selectable, not default)
-//   blind_rotate_cl2_kernel  ONE gate on a 2-CTA thread-block cluster (waves of 34..74 gates)          } data exchanged over DSMEM
-//   blind_rotate_cl4_kernel  ONE gate on a 4-CTA thread-block cluster (waves of up to 33 gates)        } with st.async + mbarrier
+// kernels_v2.cu -- the GINX blind rotation of ONE gate on a 2-CTA thread-block cluster, on 16-value / 8-value register tiles
+// (STD128_OPT shape: N = 1024, dG = 4, Bg = 2^7; waves of 34..74 gates; data exchanged over DSMEM with st.async + mbarrier).
 // Same arithmetic as blind_rotate_kernel in kernels.cu (the reference reaches it through
-// BinFHEContext::EvalBinGate, src/gate.cpp:133,172,200-202 in /root/reference), different mappings to the SM.  The throughput form:
+// BinFHEContext::EvalBinGate, src/gate.cpp:133,172,200-202 in /root/reference), a different mapping to the SM.
 //
-//  * 16 warps per CTA instead of 8 (<= 128 registers per thread): every transform works on 16-value register tiles
-//    (three passes 4 + 3 + 3 stages with two in-place shared-memory transposes) instead of 32-value tiles.  Four warps
-//    per scheduler hide the fixed IMAD / IMAD.HI latencies that left the FMA-heavy pipe 27 % idle with two.
-//  * A CTA still carries 4 gates, but as two independent PAIRS of gates (8 warps each) that only meet at named
-//    barriers of their own pair: one pair's external product overlaps the other pair's transforms.
-//  * Per gate and accumulator component two warps: the inverse transform is split across them (64-thread named
-//    barrier), then each runs two of the four digit transforms on its own.
-//  * The accumulator lives in shared memory in "centred + digit offset" form (what the digit extraction consumes).
-//  * One shared-memory layout (phys()) serves all three register-tile shapes conflict-free: 32-bit column access,
-//    64-bit pair access, 128-bit row access (checked by tools/smem_layout_check.py).
-//  * Measured and not kept (git history: "Experiment: one digit transform per warp on the FP64 pipe"): running one of each
-//    warp's two digit transforms in exact double arithmetic on the FP64 pipe was bit-exact but 11 % slower.
-//    tools/pipe_probe.cu / tools/bfly_probe.cu show why: DFMA co-issues freely with IMAD but contends with IMAD.HI and
-//    IMAD.WIDE (the 64-bit-product forms appear to use the FP64 multiplier), so there is no idle pipe to move butterflies to.
+// History (git): this file also held a 16-warp four-gates-per-CTA throughput kernel (two independent pairs of gates per CTA, 16-value
+// tiles) and a row-split 4-CTA cluster kernel.  The throughput form never beat kernels.cu's (79.5 k vs 79.0 k gates/s on all-NAND
+// batches, 76.7 k vs 77.5 k in bench.py's mix: bound by its per-pair barrier chain) and cost a second 65.8 MB key copy
+// on every context; the row-split 4-CTA form (1.17 ms per wave) is superseded by the slot-sliced one in kernels_cl.cu (1.02 ms).  Both
+// were removed in round 2.  What remains of the shared machinery: one shared-memory row layout (phys()) that serves 32-bit column,
+// 64-bit pair and 128-bit row access conflict-free (tools/smem_layout_check.py), and the 16- / 8-value tile transforms.
 #include "common.hpp"
 #include <cuda_runtime.h>
 #include <type_traits>
@@ -26,7 +16,7 @@
 namespace bfhe {
 namespace v2 {
 
-constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, G = 4, NPAD = 512, THREADS = 512;
+constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, NPAD = 512;
 constexpr u32 DIGIT_OFF = 64u + (64u << 7) + (64u << 14) + (64u << 21);
 constexpr u32 SOLINAS_Q = (1u << 27) - (1u << 11) + 1;
 
@@ -216,298 +206,11 @@ __device__ __forceinline__ void row_store(u32 *buf, const u32 (&x)[16], int T3) 
   for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(buf + (b ^ (4 * c))) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
 }
 
-// forward transform of digit l of the accumulator component published in dp[] (centred + DIGIT_OFF, natural order), by ONE
-// warp (two 16-value tiles per pass); the result (bit-reversed evaluation order, lazy < 21Q) lands in row `buf`.
-// Digits l0 and l0 + 1 are transformed TOGETHER, tile by tile: the two tiles share the accumulator words they are cut from and
-// every per-thread twiddle, and give the scheduler 16 independent butterflies per stage instead of 8.
-__device__ __forceinline__ void ntt_forward_2digits(const u32 *dp, int l0, u32 *bufA, u32 *bufB, const DevConst &P, const Tabs &tt, int lane, u32 Z) {
-  const u32 Q = P.Q, Q2 = P.Q2, qoff = P.Q - (1u << (LOGBG - 1)); // Z: a zero the compiler cannot see (add3)
-  const int sh = LOGBG * l0;
-#pragma unroll 1
-  for (int it = 0; it < 2; it++) { // wide pass: positions T + 64k, stages with 1, 2, 4, 8 groups (uniform twiddles: constant bank)
-    const int T = 32 * it + lane;
-    u32 xa[16], xb[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      // digit - B/2 + Q: congruent to the signed digit, lazy in (Q - B/2, Q + B/2) -- the transform needs no canonical input
-      const u32 d = dp[T + 64 * k] >> sh;
-      xa[k] = (d & ((1u << LOGBG) - 1)) + qoff;
-      xb[k] = ((d >> LOGBG) & ((1u << LOGBG) - 1)) + qoff;
-    }
-    ct_stages<8, 1, (BFHE_V2_SOL_FW & 15)>(xa, P.tw, P.tws, Q, Q2, Z);
-    ct_stages<8, 1, (BFHE_V2_SOL_FW & 15)>(xb, P.tw, P.tws, Q, Q2, Z);
-    col_store(bufA, xa, T);
-    col_store(bufB, xb, T);
-  }
-  __syncwarp();
-#pragma unroll 1
-  for (int it = 0; it < 2; it++) { // middle pass, in place
-    const int T = 32 * it + lane;
-    u32 xa[16], xb[16], w[16], ws[16];
-    load_tw_mid(tt.fw, w, T >> 2);
-    load_tw_mid(tt.fws, ws, T >> 2);
-    mid_load(bufA, xa, T);
-    mid_load(bufB, xb, T);
-    ct_stages<8, 2, ((BFHE_V2_SOL_FW >> 4) & 7)>(xa, w, ws, Q, Q2, Z);
-    ct_stages<8, 2, ((BFHE_V2_SOL_FW >> 4) & 7)>(xb, w, ws, Q, Q2, Z);
-    mid_store(bufA, xa, T);
-    mid_store(bufB, xb, T);
-  }
-  __syncwarp();
-#pragma unroll 1
-  for (int it = 0; it < 2; it++) { // narrow pass, in place
-    const int T = 32 * it + lane;
-    u32 xa[16], xb[16], w[16], ws[16];
-    load_tw_narrow(tt.fw, w, T);
-    load_tw_narrow(tt.fws, ws, T);
-    row_load(bufA, xa, T);
-    row_load(bufB, xb, T);
-    ct_stages<4, 1, ((BFHE_V2_SOL_FW >> 7) & 7)>(xa, w, ws, Q, Q2, Z);
-    ct_stages<4, 1, ((BFHE_V2_SOL_FW >> 7) & 7)>(xb, w, ws, Q, Q2, Z);
-    row_store(bufA, xa, T);
-    row_store(bufB, xb, T);
-  }
-}
 
-// inverse transform (unscaled; the keys carry N^-1) of row `buf` (values < B0*Q) by TWO warps, T = 32*h + lane; on return
-// x[k] = coefficient T + 64k, fully reduced.  bar_id: named barrier of this warp pair.
-template <int B0> __device__ __forceinline__ void ntt_inverse_split(u32 (&x)[16], u32 *buf, const DevConst &P, const Tabs &tt, int T, int bar_id, u32 Z) {
-  const u32 Q = P.Q;
-  {
-    u32 w[16], ws[16];
-    load_tw_narrow(tt.iw, w, T);
-    load_tw_narrow(tt.iws, ws, T);
-    row_load(buf, x, T);
-    Gs<1, 4, B0, 16, (BFHE_V2_SOL_INV & 7)>::run(x, w, ws, Q, Z);
-    row_store(buf, x, T);
-  }
-  constexpr int B1 = gs_bound(1, 4, B0, 16);
-  bar_sync(bar_id, 64);
-  {
-    u32 w[16], ws[16];
-    load_tw_mid(tt.iw, w, T >> 2);
-    load_tw_mid(tt.iws, ws, T >> 2);
-    mid_load(buf, x, T);
-    Gs<2, 8, B1, 16, ((BFHE_V2_SOL_INV >> 3) & 7)>::run(x, w, ws, Q, Z);
-    mid_store(buf, x, T);
-  }
-  constexpr int B2 = gs_bound(2, 8, B1, 16);
-  bar_sync(bar_id, 64);
-  col_load(buf, x, T);
-  Gs<1, 8, B2, 32, ((BFHE_V2_SOL_INV >> 6) & 15)>::run(x, P.itw, P.itws, Q, Z);
-#pragma unroll
-  for (int k = 0; k < 16; k++) x[k] = csub(lazy_reduce(x[k], Q), Q);
-}
 
 // table of (psi^k - 1): the lanes of a warp own slots whose exponents differ in bits 4..8, so entry k is stored at the
 // 11-bit rotation of k by 5 (bank = bits 5..9 of k): 1.5 wavefronts per gather on average instead of 16
 __host__ __device__ __forceinline__ u32 f_index(u32 k) { return ((k >> 5) & 63u) | ((k & 31u) << 6); }
-
-struct Cfg {
-  static constexpr size_t dct_words = (size_t)G * ROWS * N;  // [gate][row][phys]
-  static constexpr size_t dp_words = (size_t)G * 2 * N;      // [gate][component][natural]
-  static constexpr size_t tw_words = 4 * N;                  // fw | fws | iw | iws
-  static constexpr size_t f_words = 2 * N;                   // (psi^k - 1) in Montgomery form
-  static constexpr size_t smem_bytes = (dct_words + dp_words + tw_words + f_words) * 4 + (size_t)G * NPAD * 2;
-};
-
-__global__ void __launch_bounds__(THREADS, 1)
-blind_rotate_v2_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count, const u32 *__restrict__ bk,
-                       const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  u32 *dct = reinterpret_cast<u32 *>(smem_raw);
-  u32 *dpb = dct + Cfg::dct_words;
-  u32 *s_tw = dpb + Cfg::dp_words;
-  u32 *s_F = s_tw + Cfg::tw_words;
-  u16 *s_idx = reinterpret_cast<u16 *>(s_F + Cfg::f_words);
-  __shared__ u32 s_b[G];
-  __shared__ u32 s_zero;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pair = warp >> 3, g = warp >> 2, c = (warp >> 1) & 1, h = warp & 1; // g = gate within the CTA (2*pair + 0/1)
-  const int gate0 = blockIdx.x * G;
-  const int gcount = min(G, count - gate0);
-  const u32 Q = P.Q, q = P.q, n = P.n;
-  const int pair_bar = 1 + pair, poly_bar = 3 + (warp >> 1);
-
-  if (tid == 0) s_zero = 0;
-  for (int i = tid; i < (int)Cfg::tw_words; i += THREADS) s_tw[i] = g_tw[i];
-  for (int i = tid; i < 2 * N; i += THREADS) s_F[i] = g_F[i];
-  const Tabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
-
-  // ---- prologue: LWE prep (EvalBinGate's ct1+ct2 / 2(ct1-ct2) / Bootstrap's b+q/4, with fused EvalNOT), as in kernels.cu ----
-  for (int gg = 0; gg < gcount; gg++) {
-    const DevGate dg = gates[gate0 + gg];
-    const u32 gate = dg.op & 0xff;
-    for (u32 i = tid; i <= n; i += THREADS) {
-      u32 x = dg.in0[i];
-      if (dg.op & OP_NEG0) x = (i == n) ? (q / 4 + q - x) % q : (q - x) % q;
-      u32 v;
-      if (gate == OP_BOOTSTRAP) {
-        v = (i == n) ? (x + q / 4) % q : x;
-      } else {
-        u32 y = dg.in1[i];
-        if (dg.op & OP_NEG1) y = (i == n) ? (q / 4 + q - y) % q : (q - y) % q;
-        v = (gate == OP_XOR_FAST || gate == OP_XNOR_FAST) ? (2 * (x + q - y)) % q : (x + y) % q;
-      }
-      if (i == n) s_b[gg] = v;
-      else s_idx[gg * NPAD + i] = (u16)(((q - v) % q) * P.factor); // monomial exponent in [0,2N)
-    }
-  }
-  __syncthreads();
-
-  const u32 Z = *(volatile u32 *)&s_zero; // a zero ptxas cannot see through (add3)
-  // ---- accumulator init: acc = (0, testvector), published as centred + DIGIT_OFF ----
-  const bool gvalid = g < gcount;
-  const int T = 32 * h + lane; // logical thread of this warp pair's polynomial
-  u32 *mydp = dpb + ((size_t)g * 2 + c) * N;
-  u32 *myrow = dct + ((size_t)g * ROWS + c) * N; // R[g][c] aliases dct row c of gate g
-  if (gvalid) {
-    u32 q1 = 0, q2 = 0, b = 0;
-    if (c == 1) {
-      const u32 gate = gates[gate0 + g].op & 0xff;
-      q1 = P.gate_const[gate == OP_BOOTSTRAP ? OP_AND : gate];
-      q2 = (q1 + q / 2) % q;
-      b = s_b[g];
-    }
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      const u32 idx = T + 64 * k;
-      u32 v = DIGIT_OFF;
-      if (c == 1 && idx % P.factor == 0) {
-        const u32 t = (b + q - idx / P.factor) % q;
-        const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
-        v = in ? DIGIT_OFF - P.Q8 : DIGIT_OFF + P.Q8; // -(Q/8+1) / +(Q/8+1), centred
-      }
-      mydp[idx] = v;
-    }
-  }
-
-  // ---- external product: thread tp of the pair owns the 4 evaluation slots stored at words 4*tp .. 4*tp+3 of every row ----
-  const int tp = tid & 255;
-  u32 ex[4];
-#pragma unroll
-  for (int r = 0; r < 4; r++) ex[r] = 2 * (__brev((u32)unphys(4 * tp + r)) >> (32 - LOGN)) + 1; // slot = X -> psi^ex
-  const int pg0 = 2 * pair, pgn = max(0, min(2, gcount - pg0)); // this pair's gates
-  const u32 qinv = P.qinv_neg;
-
-  auto close_step = [&]() { // inverse transform of the previous product, accumulate, publish
-    u32 x[16];
-    ntt_inverse_split<2>(x, myrow, P, tt, T, poly_bar, Z);
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      // centred(acc) + x, x in [0,Q): one conditional subtraction of Q re-centres it with exactly the reference's rule
-      // (t < Q>>1 stays t, otherwise t - Q), see the case analysis in DESIGN.md 5.1c
-      const u32 s = mydp[T + 64 * k] + x[k];
-      mydp[T + 64 * k] = (s >= DIGIT_OFF + (Q >> 1)) ? s - Q : s;
-    }
-  };
-
-#ifdef BFHE_PHASE_TIMING
-  long long tph[5] = {0, 0, 0, 0, 0}, tc0, tc1;
-#define PH_T(i) do { tc1 = clock64(); tph[i] += tc1 - tc0; tc0 = tc1; } while (0)
-  tc0 = clock64();
-#else
-#define PH_T(i)
-#endif
-  for (u32 step = 0; step < n; step++) {
-    // ================= phase A: transforms (integer pipes) =================
-    if (gvalid) {
-      if (step > 0) close_step();
-      bar_sync(poly_bar, 64); // both halves of dp visible; nobody still reads row c
-      PH_T(0);
-      ntt_forward_2digits(mydp, 2 * h, dct + ((size_t)g * ROWS + c + 4 * h) * N, dct + ((size_t)g * ROWS + c + 4 * h + 2) * N, P, tt, lane, Z);
-    }
-    PH_T(1);
-    const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + 4 * tp;
-    {
-      uint4 kr[2][ROWS];
-      if (pgn > 0) {
-#pragma unroll
-        for (int s = 0; s < 2; s++)
-#pragma unroll
-          for (int r = 0; r < ROWS; r++) kr[s][r] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((s * ROWS + r) * 2 + 0) * N));
-      }
-      bar_sync(pair_bar, 256);
-      PH_T(2);
-      // ================= phase B: external product =================
-      u32 out0[2][4], fpn[2][2][4];
-#pragma unroll
-      for (int gl = 0; gl < 2; gl++) { // (X^m - 1), (X^-m - 1) at this thread's four slots, Montgomery form
-        if (gl >= pgn) continue;
-        const u32 m = s_idx[(pg0 + gl) * NPAD + step];
-#pragma unroll
-        for (int sl = 0; sl < 4; sl++) {
-          const u32 y = m * ex[sl], ny = 0u - y;
-          fpn[gl][0][sl] = s_F[f_index(y)];
-          fpn[gl][1][sl] = s_F[f_index(ny)];
-        }
-      }
-#pragma unroll
-      for (int cc = 0; cc < 2; cc++) {
-        if (cc == 1 && pgn > 0) {
-#pragma unroll
-          for (int s = 0; s < 2; s++)
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) kr[s][r] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((s * ROWS + r) * 2 + 1) * N));
-        }
-#pragma unroll
-        for (int gl = 0; gl < 2; gl++) {
-          if (gl >= pgn) continue;
-          u32 *gd = dct + (size_t)(pg0 + gl) * ROWS * N + 4 * tp;
-          u64 sp[4] = {0, 0, 0, 0}, sn[4] = {0, 0, 0, 0};
-#pragma unroll
-          for (int r = 0; r < ROWS; r++) {
-            const uint4 dv = *reinterpret_cast<const uint4 *>(gd + (size_t)r * N);
-            const uint4 kp = kr[0][r], kn = kr[1][r];
-            sp[0] += (u64)dv.x * kp.x; sp[1] += (u64)dv.y * kp.y; sp[2] += (u64)dv.z * kp.z; sp[3] += (u64)dv.w * kp.w;
-            sn[0] += (u64)dv.x * kn.x; sn[1] += (u64)dv.y * kn.y; sn[2] += (u64)dv.z * kn.z; sn[3] += (u64)dv.w * kn.w;
-          }
-          u32 out[4];
-#pragma unroll
-          for (int sl = 0; sl < 4; sl++)
-            out[sl] = redc((u64)redc(sp[sl], Q, qinv) * fpn[gl][0][sl] + (u64)redc(sn[sl], Q, qinv) * fpn[gl][1][sl], Q, qinv);
-          if (cc == 0) {
-#pragma unroll
-            for (int sl = 0; sl < 4; sl++) out0[gl][sl] = out[sl];
-          } else { // R[g][0], R[g][1] overwrite rows 0 and 1: this thread has consumed these four slots of every row
-            *reinterpret_cast<uint4 *>(gd) = make_uint4(out0[gl][0], out0[gl][1], out0[gl][2], out0[gl][3]);
-            *reinterpret_cast<uint4 *>(gd + (size_t)N) = make_uint4(out[0], out[1], out[2], out[3]);
-          }
-        }
-      }
-    }
-    PH_T(3);
-    bar_sync(pair_bar, 256);
-    PH_T(4);
-  }
-
-  // ---- epilogue: last inverse transform, sample extraction (a14) and ModSwitch Q -> qKS (a15) ----
-  if (gvalid) {
-    if (n > 0) close_step();
-    const size_t gi = (size_t)gate0 + g;
-    u32 *e = ext + gi * (N + 4);
-    const u64 qKS = P.qKS;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      const u32 j = T + 64 * k;
-      u32 a = mydp[j] - DIGIT_OFF;
-      a += ((int)a < 0) ? Q : 0u;
-      if (acc_dbg) acc_dbg[(gi * 2 + c) * N + j] = a;
-      if (c == 0) {
-        const u32 v = (j == 0) ? a : (a == 0 ? 0 : Q - a); // Transpose: a'_0 = a_0, a'_k = -a_{N-k}
-        e[(j == 0) ? 0 : N - j] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
-      } else if (j == 0) {
-        const u32 v = csub(a + P.Q8, Q);
-        e[N] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
-      }
-    }
-#ifdef BFHE_PHASE_TIMING
-    if (acc_dbg && lane == 0)
-      for (int i = 0; i < 5; i++) acc_dbg[(gi * 2 + c) * N + 32 + 8 * h + i] = (u32)(tph[i] / 1000); // kilo-cycles
-#endif
-  }
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // Latency form on a 2-CTA thread-block cluster: ONE gate on TWO SMs (narrow circuit wavefronts: fewer gates than half the
@@ -802,7 +505,10 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
 
 #ifdef BFHE_PHASE_TIMING
   long long tph[5] = {0, 0, 0, 0, 0}, tc0, tc1;
+#define PH_T(i) do { tc1 = clock64(); tph[i] += tc1 - tc0; tc0 = tc1; } while (0)
   tc0 = clock64();
+#else
+#define PH_T(i)
 #endif
   // Data moves between the two CTAs as st.async pushes counted on the RECEIVER's mbarrier, so the step loop contains no
   // cluster-scope fence (barrier.cluster.arrive.release alone cost ~1000 cycles per use here).  Order of events, CTA r:
@@ -920,208 +626,9 @@ blind_rotate_cl2_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   cluster_sync_all(); // a CTA must not exit while its peer may still push into its shared memory
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// ONE gate on FOUR SMs (4-CTA cluster) for wavefronts of at most a quarter of the SMs.  Rank r: component c = r & 1, half s = r >> 1.
-//   * both CTAs of a component keep the accumulator and run the inverse transform of its product row (redundantly: it is the
-//     serial part of a step and costs nothing extra in time);
-//   * CTA (c, s) transforms digits 2s and 2s + 1 of component c (two warps per row) and pushes every finished 16-word tile to the
-//     CTA that owns its quarter of the evaluation slots (possibly itself) -- st.async counted on the receiver's mbarrier;
-//   * every CTA multiplies its quarter of the slots against its quarter of the step's key tile (32 KB, TMA) and pushes the two
-//     product components to the two CTAs of each component.
-// Same write-after-read argument as the 2-CTA form: a receiver's buffers are overwritten only by pushes that causally follow the
-// last read of the previous contents (rows(s+1) follow the owner's inverse transform, which needed every CTA's product(s)).
-// ------------------------------------------------------------------------------------------------------------------
-struct Cl4Cfg {
-  static constexpr int THREADS = 256, QUARTER = N / 4, KEYPOLYS = 2 * ROWS * 2;
-  static constexpr u32 KEYBYTES = (u32)KEYPOLYS * QUARTER * 4;
-  // words: all 8 digit rows at my slots [ROWS][QUARTER] | transform scratch [2][N] | product row [N] | dp [N] | twiddles [4N] | F [2N] |
-  // key tile [KEYPOLYS][QUARTER]; then u16 idx[NPAD]; then three mbarriers (key tile, digit rows, product)
-  static constexpr size_t words = (size_t)ROWS * QUARTER + 2 * N + N + N + 4 * N + 2 * N + (size_t)KEYPOLYS * QUARTER;
-  static constexpr size_t smem_bytes = words * 4 + NPAD * 2 + 32;
-  static constexpr u32 ROWS_TX = (u32)ROWS * QUARTER * 4, PROD_TX = (u32)N * 4; // bytes pushed to a CTA per step (own pushes included)
-};
-
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(Cl4Cfg::THREADS, 1)
-blind_rotate_cl4_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count, const u32 *__restrict__ bk,
-                        const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
-  constexpr int QUARTER = Cl4Cfg::QUARTER, KEYPOLYS = Cl4Cfg::KEYPOLYS;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  u32 *stage = reinterpret_cast<u32 *>(smem_raw);  // [ROWS][QUARTER]: row c + 2l of the digit transforms at MY quarter of the slots
-  u32 *frow = stage + (size_t)ROWS * QUARTER;      // [2][N]: in-place scratch of my two digit transforms
-  u32 *prow = frow + 2 * N;                        // [N]: product row of my component, pushed by all four CTAs
-  u32 *dp = prow + N;                              // centred accumulator + DIGIT_OFF, natural order
-  u32 *s_tw = dp + N;
-  u32 *s_F = s_tw + 4 * N;
-  u32 *s_key = s_F + 2 * N;                        // [sign][row][cc][QUARTER]
-  u16 *s_idx = reinterpret_cast<u16 *>(s_key + (size_t)KEYPOLYS * QUARTER);
-  u64 *s_bar = reinterpret_cast<u64 *>(s_idx + NPAD); // [0] key tile (TMA), [1] digit rows, [2] product row
-  __shared__ u32 s_b, s_zero;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const u32 r = cluster_rank(), c = r & 1u, sub = r >> 1;
-  const size_t gi = blockIdx.x >> 2;
-  const u32 Q = P.Q, q = P.q, n = P.n;
-  const DevGate dg = gates[gi];
-
-  if (tid == 0) {
-    s_zero = 0;
-    mbar_init(s_bar + 0, 1);
-    mbar_init(s_bar + 1, 1);
-    mbar_init(s_bar + 2, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < 4 * N; i += Cl4Cfg::THREADS) s_tw[i] = g_tw[i];
-  for (int i = tid; i < 2 * N; i += Cl4Cfg::THREADS) s_F[i] = g_F[i];
-  const Tabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
-  { // LWE prep, as in the other kernels (all four CTAs compute it)
-    const u32 gate = dg.op & 0xff;
-    for (u32 i = tid; i <= n; i += Cl4Cfg::THREADS) {
-      u32 x = dg.in0[i];
-      if (dg.op & OP_NEG0) x = (i == n) ? (q / 4 + q - x) % q : (q - x) % q;
-      u32 v;
-      if (gate == OP_BOOTSTRAP) v = (i == n) ? (x + q / 4) % q : x;
-      else {
-        u32 y = dg.in1[i];
-        if (dg.op & OP_NEG1) y = (i == n) ? (q / 4 + q - y) % q : (q - y) % q;
-        v = (gate == OP_XOR_FAST || gate == OP_XNOR_FAST) ? (2 * (x + q - y)) % q : (x + y) % q;
-      }
-      if (i == n) s_b = v;
-      else s_idx[i] = (u16)(((q - v) % q) * P.factor);
-    }
-  }
-  __syncthreads();
-  const u32 Z = *(volatile u32 *)&s_zero;
-  auto issue_keys = [&](u32 step) { // key copy of this kernel: [step][rank][polynomial][QUARTER]: 32 KB contiguous per CTA and step
-    if (lane == 0) mbar_expect_tx(s_bar, Cl4Cfg::KEYBYTES);
-    __syncwarp();
-    const u32 *src = bk + ((size_t)step * 4 + r) * KEYPOLYS * QUARTER;
-    if (lane < 2) bulk_g2s(s_key + (size_t)lane * 4096, src + (size_t)lane * 4096, 16384, s_bar);
-  };
-  static_assert(Cl4Cfg::KEYBYTES == 2 * 16384, "two bulk copies");
-  if (warp == 7 && n > 0) issue_keys(0);
-  { // accumulator init: component 0 = 0, component 1 = test vector
-    u32 q1 = 0, q2 = 0, b = 0;
-    if (c == 1) {
-      const u32 gate = dg.op & 0xff;
-      q1 = P.gate_const[gate == OP_BOOTSTRAP ? OP_AND : gate];
-      q2 = (q1 + q / 2) % q;
-      b = s_b;
-    }
-    for (u32 idx = tid; idx < (u32)N; idx += Cl4Cfg::THREADS) {
-      u32 v = DIGIT_OFF;
-      if (c == 1 && idx % P.factor == 0) {
-        const u32 t = (b + q - idx / P.factor) % q;
-        const bool in = (q1 < q2) ? (t >= q1 && t < q2) : !(t >= q2 && t < q1);
-        v = in ? DIGIT_OFF - P.Q8 : DIGIT_OFF + P.Q8;
-      }
-      dp[idx] = v;
-    }
-  }
-  cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
-
-  // external product: thread t owns slot (physical word) QUARTER * r + t
-  const int o = QUARTER * (int)r + tid;
-  const u32 ex = 2 * (__brev((u32)unphys(o)) >> (32 - LOGN)) + 1;
-  // product pushes: the four lanes of a slot group (4 consecutive slots) each serve ONE destination CTA with one 16-byte push
-  // (per-slot 4-byte pushes to four destinations quadrupled the packet count and cost 0.4 ms per wave once every SM was busy)
-  const u32 dest = (u32)lane & 3u;
-  const u32 prow_dst = dsmem_addr(prow + (o & ~3), dest), prod_bar = dsmem_addr(s_bar + 2, dest);
-  const u32 qinv = P.qinv_neg;
-  // digit transforms: warps 0-1 row 0 (digit 2 sub), warps 2-3 row 1 (digit 2 sub + 1); tile T goes to the CTA owning its quarter
-  const int h = warp & 1, T = 32 * h + lane, frj = (warp >> 1) & 1, l_mine = 2 * (int)sub + frj, R_mine = (int)c + 2 * l_mine;
-  const u32 kq = (u32)(T ^ ((T >> 3) & 1)) >> 4; // quarter (= destination rank) of tile T
-  const u32 push_dst = dsmem_addr(stage, kq) + 4u * (u32)(R_mine * QUARTER) - 4u * (u32)QUARTER * kq, push_bar = dsmem_addr(s_bar + 1, kq);
-
-  auto close_step = [&]() { // warps 0-3: inverse transform of my component's product row, accumulate, publish
-    u32 x[8];
-    ntt_inverse_quad8<2>(x, prow, P, tt, tid, 5, Z);
-    const int hi = lane >> 4, T6 = 16 * warp + (lane & 15);
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const int j = T6 + 64 * (k + 8 * hi);
-      const u32 s = dp[j] + x[k];
-      dp[j] = (s >= DIGIT_OFF + (Q >> 1)) ? s - Q : s;
-    }
-  };
-
-  for (u32 step = 0; step < n; step++) {
-    if (step > 0) {
-      if (warp < 4) {
-        mbar_wait(s_bar + 2, (step - 1) & 1); // all four quarters of my product row have landed
-        close_step();
-      }
-      __syncthreads();
-    }
-    if (tid == 0) { // this step's expectations (early pushes just run the count negative)
-      mbar_expect_tx(s_bar + 1, Cl4Cfg::ROWS_TX);
-      mbar_expect_tx(s_bar + 2, Cl4Cfg::PROD_TX);
-    }
-    if (warp < 4) ntt_forward_split(dp, l_mine, frow + (size_t)frj * N, P, tt, T, 1 + frj, Z, push_dst, push_bar);
-    mbar_wait(s_bar, step & 1);
-    mbar_wait(s_bar + 1, step & 1); // all eight digit rows at my slots
-    {
-      const u32 m = s_idx[step];
-      const u32 y = m * ex, ny = 0u - y;
-      const u32 fp = s_F[f_index(y)], fn = s_F[f_index(ny)];
-      u64 sp[2] = {0, 0}, sn[2] = {0, 0}; // [cc]
-#pragma unroll
-      for (int rw = 0; rw < ROWS; rw++) {
-        const u32 d = stage[rw * QUARTER + tid];
-#pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-          sp[cc] += (u64)d * s_key[(size_t)((0 * ROWS + rw) * 2 + cc) * QUARTER + tid];
-          sn[cc] += (u64)d * s_key[(size_t)((1 * ROWS + rw) * 2 + cc) * QUARTER + tid];
-        }
-      }
-      u32 out[2];
-#pragma unroll
-      for (int cc = 0; cc < 2; cc++) out[cc] = redc((u64)redc(sp[cc], Q, qinv) * fp + (u64)redc(sn[cc], Q, qinv) * fn, Q, qinv);
-      uint4 v; // component dest & 1 (it lives in ranks dest & 1 and (dest & 1) + 2) of the group's four slots
-      const int g0 = lane & ~3;
-      {
-        const u32 a0 = __shfl_sync(0xffffffffu, out[0], g0), a1 = __shfl_sync(0xffffffffu, out[0], g0 + 1);
-        const u32 a2 = __shfl_sync(0xffffffffu, out[0], g0 + 2), a3 = __shfl_sync(0xffffffffu, out[0], g0 + 3);
-        const u32 b0 = __shfl_sync(0xffffffffu, out[1], g0), b1 = __shfl_sync(0xffffffffu, out[1], g0 + 1);
-        const u32 b2 = __shfl_sync(0xffffffffu, out[1], g0 + 2), b3 = __shfl_sync(0xffffffffu, out[1], g0 + 3);
-        v = (dest & 1u) ? make_uint4(b0, b1, b2, b3) : make_uint4(a0, a1, a2, a3);
-      }
-      st_async4(prow_dst, v, prod_bar);
-    }
-    __syncthreads(); // nobody reads the key tile any more
-    if (warp == 7 && step + 1 < n) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue_keys(step + 1);
-    }
-  }
-
-  // ---- epilogue: last inverse transform, sample extraction (a14) and ModSwitch Q -> qKS (a15); ranks 0 and 1 write the result ----
-  if (n > 0 && warp < 4) {
-    mbar_wait(s_bar + 2, (n - 1) & 1);
-    close_step();
-  }
-  __syncthreads();
-  if (sub == 0) {
-    u32 *e = ext + gi * (N + 4);
-    const u64 qKS = P.qKS;
-    for (u32 j = tid; j < (u32)N; j += Cl4Cfg::THREADS) {
-      u32 a = dp[j] - DIGIT_OFF;
-      a += ((int)a < 0) ? Q : 0u;
-      if (acc_dbg) acc_dbg[(gi * 2 + c) * N + j] = a;
-      if (c == 0) {
-        const u32 v = (j == 0) ? a : (a == 0 ? 0 : Q - a); // Transpose: a'_0 = a_0, a'_k = -a_{N-k}
-        e[(j == 0) ? 0 : N - j] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
-      } else if (j == 0) {
-        const u32 v = csub(a + P.Q8, Q);
-        e[N] = (qKS == Q) ? v : (u32)(((2 * (u64)v * qKS + Q) / (2 * (u64)Q)) % qKS);
-      }
-    }
-  }
-  cluster_sync_all(); // a CTA must not exit while its peers may still push into its shared memory
-}
-
 // key copy of the cluster kernels: [step][polynomial][N] -> [step][quarter][polynomial][N/4]
 __global__ void bk_split_cl4_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t nsteps) {
-  constexpr int KP = Cl4Cfg::KEYPOLYS, QUARTER = Cl4Cfg::QUARTER;
+  constexpr int KP = Cl2Cfg::KEYPOLYS, QUARTER = N / 4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsteps * KP * N; i += (size_t)gridDim.x * blockDim.x) {
     const size_t step = i / ((size_t)KP * N), rem = i % ((size_t)KP * N);
     const int pl = (int)(rem / N), o = (int)(rem % N), rk = o / QUARTER;
@@ -1144,10 +651,7 @@ bool v2_supported(const DevConst &P, int method_ap) {
   return !method_ap && P.N == 1024 && P.dG == 4 && P.logBG == 7 && P.Q == v2::SOLINAS_Q && P.n <= (u32)v2::NPAD;
 }
 int v2_set_attrs() {
-  int rc = (int)cudaFuncSetAttribute(v2::blind_rotate_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cfg::smem_bytes);
-  rc |= (int)cudaFuncSetAttribute(v2::blind_rotate_cl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cl2Cfg::smem_bytes);
-  rc |= (int)cudaFuncSetAttribute(v2::blind_rotate_cl4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cl4Cfg::smem_bytes);
-  return rc;
+  return (int)cudaFuncSetAttribute(v2::blind_rotate_cl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::Cl2Cfg::smem_bytes);
 }
 template <typename K> static int max_active_clusters(K kern, int cluster, int threads, size_t smem) {
   if (v2_set_attrs()) return 0;
@@ -1181,28 +685,9 @@ static int current_device_slot() { // the limits are per device (one process may
   cudaGetDevice(&dev);
   return dev >= 0 && dev < 64 ? dev : 0;
 }
-int cl4_max_gates() {
-  static int cached[64];
-  static bool have[64];
-  const int d = current_device_slot();
-  if (!have[d]) { cached[d] = max_active_clusters(v2::blind_rotate_cl4_kernel, 4, v2::Cl4Cfg::THREADS, v2::Cl4Cfg::smem_bytes); have[d] = true; }
-  return cached[d];
-}
-// The 4-CTA form slows down when (almost) every SM carries a cluster: measured on B200 1.19 ms up to 30 gates, 1.26 ms for 31-33,
-// 1.59 ms for 34-37 (37 = co-resident maximum) -- above ~7/8 of the maximum the 2-CTA form (1.49 ms up to 74 gates) is the better one.
-int cl4_fast_gates() { const int m = cl4_max_gates(); return m - m / 8; }
 int launch_bk_split_cl4(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
   if (npoly == 0) return 0;
-  v2::bk_split_cl4_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly / v2::Cl4Cfg::KEYPOLYS);
-  return (int)cudaGetLastError();
-}
-int launch_blind_rotate_cl4(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
-                            LaunchInfo *info) {
-  if (count <= 0) return 0;
-  if (int rc = v2_attrs_once()) return rc;
-  if (info) { info->gates_per_cta = 1; info->ctas = 4 * count; info->smem_bytes = v2::Cl4Cfg::smem_bytes; }
-  v2::blind_rotate_cl4_kernel<<<4 * count, v2::Cl4Cfg::THREADS, v2::Cl4Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk4, vb.d_tw2,
-                                                                                                         vb.d_F, d_ext, d_acc_dbg);
+  v2::bk_split_cl4_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly / v2::Cl2Cfg::KEYPOLYS);
   return (int)cudaGetLastError();
 }
 // how many gates the cluster form runs at once (2-CTA clusters must sit inside one GPC, so this can be less than SMs / 2)
@@ -1227,15 +712,4 @@ int launch_bk_permute_v2(const u32 *d_src, u32 *d_dst, size_t npoly, void *strea
   v2::bk_permute_v2_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly);
   return (int)cudaGetLastError();
 }
-int launch_blind_rotate_v2(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
-                           LaunchInfo *info) {
-  if (count <= 0) return 0;
-  if (int rc = v2_attrs_once()) return rc;
-  const int ctas = (count + v2::G - 1) / v2::G;
-  if (info) { info->gates_per_cta = v2::G; info->ctas = ctas; info->smem_bytes = v2::Cfg::smem_bytes; }
-  v2::blind_rotate_v2_kernel<<<ctas, v2::THREADS, v2::Cfg::smem_bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bk2, vb.d_tw2, vb.d_F, d_ext,
-                                                                                           d_acc_dbg);
-  return (int)cudaGetLastError();
-}
-
 } // namespace bfhe

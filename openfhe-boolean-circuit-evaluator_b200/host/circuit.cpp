@@ -579,8 +579,8 @@ static int probe_costs(bfhe_circuit *c) {
     cudaEvent_t e0, e1;
     BFHE_CUDA(cudaEventCreate(&e0));
     BFHE_CUDA(cudaEventCreate(&e1));
-    const int force[4] = {64, 32, 8, 4};
-    const int count[4] = {std::min(f.cl4, cl4_fast_gates()), std::min(f.cl2, cl2_max_gates()), f.sms, 4 * f.sms};
+    const int force[4] = {128, 32, 8, 4};
+    const int count[4] = {std::min(f.cl4, clx_fast_gates()), std::min(f.cl2, cl2_max_gates()), f.sms, 4 * f.sms};
     const double dflt[4] = {FormCosts().cl4, FormCosts().cl2, FormCosts().lat, FormCosts().thr};
     for (int k = 0; k < 4; k++) {
       x->form_cost_ms[k] = dflt[k];
