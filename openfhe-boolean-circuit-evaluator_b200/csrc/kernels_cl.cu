@@ -18,20 +18,24 @@
 //     out per CTA and step); every CTA then finishes the inverse transform redundantly (two cross-block stages), adds to its copy of the
 //     accumulator and cuts the next digits.
 //
-// Third revision (round 2): DSMEM moves ~20 bytes per cycle and SM, so the 6 KB exchange alone is ~300 cycles of a ~4 000-cycle step, and
-// in the second revision every phase was fenced from the next by a CTA barrier.  Here the step is two pipelines, one per accumulator
-// component c, that meet only at the external product:
-//   * warps 4 c .. 4 c + 3 ("group c", 128 threads, one warp per scheduler) own component c: they hold its 1 024 coefficients in registers, run the
-//     cross-block inverse stages for it as soon as ITS partial values have landed (one mbarrier per component and step parity), publish
-//     centred + offset words in shared memory, and -- after a 128-thread named barrier -- each warp cuts its own digit row out of them
-//     (warp 4 c + l transforms row c + 2 l), looks the products up and runs the row's sub-transform straight from registers;
-//   * the product is computed component 0 first: every thread runs the five inverse stages that stay inside its warp (shuffles) and
-//     stores the value into the CTA's own row of the receive buffer; a ninth warp then sends that 1 KB row to the three peers with one
-//     TMA bulk copy each (shared::cta -> shared::cluster, counted on the receiver's mbarrier).  Component 0 is on the wire while the
-//     main warps still multiply component 1, and group 0 is already transforming while component 1 is in flight;
-//   * the three remaining stages of the 256-point inverse sub-transforms run AFTER the exchange, on all four rows at once (warp l of
-//     group c takes the row that came from CTA l), instead of on one warp before it: measured, the single-warp stage plus the hand-off
-//     to it cost ~700 cycles of every step's critical path against ~150 for the redundant arithmetic.
+// Third revision (round 2).  In the second revision every phase was fenced from the next by a CTA barrier, one warp per component ran the
+// last inverse stages before the exchange, and the key words came through LDG into registers (which stalled the look-up phase behind
+// the loads once 30 clusters shared the L2).  Now:
+//   * warps 4 c .. 4 c + 3 ("group c", 128 threads, one warp per scheduler) own accumulator component c: they hold its 1 024 coefficients
+//     in registers, and everything that concerns only that component is ordered by 128-thread named barriers and by the component's own
+//     mbarrier: the cross-block inverse stages, publishing centred + offset words in shared memory, cutting digit row c + 2 l out of them
+//     (warp 4 c + l), the table look-ups and that row's sub-transform straight from registers.  The two groups meet once per step, at the
+//     barrier in front of the external product;
+//   * the product is split by component as well: group c computes component c at two adjacent slots per thread, which makes the first
+//     inverse stage a register operation and the next five shuffles on two independent values; every thread then pushes its two values to
+//     the three peers itself (8-byte st.async counted on the receiver's mbarrier) -- measured against TMA bulk copies of the finished 1 KB
+//     row by a dedicated warp (shared::cta -> shared::cluster): 0.975 vs 1.000 ms, the hand-off to an issuing warp (barrier, proxy fence,
+//     three copies) cost ~300 cycles of every step's critical path;
+//   * the two remaining stages of the 256-point inverse sub-transforms run AFTER the exchange, on all four rows at once (warp l of group c
+//     takes the row that came from CTA l);
+//   * a ninth warp fetches the key tiles (32 KB per step and CTA, two TMA bulk copies, two steps ahead, double buffered); the product
+//     reads them with one conflict-free LDS.128 per four rows.
+// Per-step timeline and phase costs: tools/phase_timing.py (build with -DBFHE_PHASE_TIMING), profiles/r2_clx_*.
 // No cluster-scope fence or barrier.cluster inside the step loop; receive buffers and their mbarriers alternate by step parity, so a
 // CTA that runs one step ahead cannot overwrite or miscount data its peer is still reading.
 #include "common.hpp"
@@ -40,7 +44,7 @@
 namespace bfhe {
 namespace clx {
 
-constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, NPAD = 512, R = 4, NB = N / R, THREADS = 288; // 8 main warps + the warp that issues the bulk copies
+constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, NPAD = 512, R = 4, NB = N / R, THREADS = 288; // 8 main warps + the warp that fetches the key tiles
 constexpr int KEYPOLYS = 2 * ROWS * 2;
 constexpr u32 DIGIT_OFF = 64u + (64u << 7) + (64u << 14) + (64u << 21);
 constexpr u32 SOLINAS_Q = (1u << 27) - (1u << 11) + 1;
@@ -99,16 +103,11 @@ __device__ __forceinline__ void st_async4(u32 dsmem, uint4 v, u32 dsmem_bar) {
                : "memory");
 }
 
-// local shared memory -> a peer CTA's shared memory, counted on the peer's mbarrier (one TMA bulk copy instead of 64 st.async)
-__device__ __forceinline__ void bulk_s2peer(u32 dsmem_dst, const void *src, u32 bytes, u32 dsmem_bar) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dsmem_dst), "r"(smem_u32(src)), "r"(bytes),
-               "r"(dsmem_bar)
+__device__ __forceinline__ void st_async2(u32 dsmem, uint2 v, u32 dsmem_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dsmem), "r"(v.x), "r"(v.y), "r"(dsmem_bar)
                : "memory");
 }
-#ifndef CLX_ISSUE_PAR
-#define CLX_ISSUE_PAR 0 // 1: the three bulk copies of a row are issued by three lanes instead of one after the other (measured: slower, 1.075 vs 1.02 ms)
-#endif
-
+__device__ __forceinline__ void mbar_arrive(u64 *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 // ---- 8-value register stages.  Stage with half-size T pairs a = g * 2T + (i % T), b = a + T and uses twiddle w[8 / (2T) + g] ----
 template <int T> __device__ __forceinline__ void ct8_stage(u32 (&x)[8], const u32 (&w)[8], const u32 (&ws)[8], u32 Q, u32 Q2) {
   u32 t[4];
@@ -185,7 +184,7 @@ constexpr u32 KEYBYTES = KEYPOLYS * NB * 4;     // this CTA's quarter of one ste
 constexpr u32 RECV_TX_C = (u32)(R - 1) * NB * 4; // bytes the three peers push into a CTA per step and component
 
 // named barriers (0 is left to __syncthreads in the prologue)
-constexpr int BAR_DCT = 1, BAR_GROUP = 2 /* + c */, BAR_PROD = 4 /* + c */;
+constexpr int BAR_DCT = 1, BAR_GROUP = 2 /* + c */, BAR_KEY = 4;
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -208,7 +207,7 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   const DevGate dg = gates[gi];
 
   if (tid == 0) {
-    for (int i = 0; i < 4; i++) mbar_init(rbar + i, 1);
+    for (int i = 0; i < 4; i++) mbar_init(rbar + i, 128); // one arrival per thread of the group that owns the component
     mbar_init(kbar + 0, 1); mbar_init(kbar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -268,58 +267,20 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
 #endif
 
   if (warp >= 8) {
-    // ================= issue warp: sends this CTA's finished rows to the peers and fetches the key tiles =================
-    if (lane == (CLX_ISSUE_PAR ? R : 0) && n > 0) {
+    // ================= ninth warp: fetches the key tiles (TMA bulk copies, two steps ahead) =================
+    if (lane == 0 && n > 0) {
       issue_keys(0);
       if (n > 1) issue_keys(1);
     }
-    // shared::cluster addresses in "my" peer (lane p < 3 serves peer (k + 1 + p) % R): receive buffer, rbar[0][0]
-    const u32 my_dest = (k + 1 + (u32)(lane < R - 1 ? lane : 0)) % R;
-    const u32 my_peer_rbuf = dsmem_addr(rbuf, my_dest), my_peer_bar = dsmem_addr(rbar, my_dest);
     cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
-    for (u32 step = 0; step < n; step++) {
-      const u32 par = step & 1;
-#ifdef BFHE_PHASE_TIMING
-      tstep = step;
-#endif
-#pragma unroll
-      for (int c = 0; c < 2; c++) {
-        bar_sync(BAR_PROD + c, 256 + 32); // all 256 product threads have stored component c (and, for c = 1, are done with the key tile)
-        CLX_T(2 * c);
-        const u32 roww = (u32)(((par * R + k) * 2 + c) * NB);
-#if CLX_ISSUE_PAR
-        if (lane < R - 1) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the writers' generic-proxy stores (ordered before me by the barrier), before the async proxy reads them
-          bulk_s2peer(my_peer_rbuf + roww * 4u, rbuf + roww, NB * 4, my_peer_bar + 16u * par + 8u * c); // lane p -> peer (k + 1 + p) % R
-        } else if (lane == R - 1) {
-          // one arrival per step and component: it releases the CTA's own row to group c and posts the bytes expected from the three
-          // peers (copies that landed earlier merely ran the count negative)
-          mbar_expect_tx(rbar + par * 2 + c, RECV_TX_C);
-        } else if (lane == R && c == 1 && step + 2 < n) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the product's reads of this key buffer, before the async proxy overwrites it
-          issue_keys(step + 2);
-        }
-#else
-        if (lane == 0) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the writers' generic-proxy stores (ordered before me by the barrier), before the async proxy reads them
-#pragma unroll
-          for (int p = 0; p < R - 1; p++)
-            bulk_s2peer(dsmem_addr(rbuf + roww, (k + 1 + p) % R), rbuf + roww, NB * 4, dsmem_addr(rbar + par * 2 + c, (k + 1 + p) % R));
-          mbar_expect_tx(rbar + par * 2 + c, RECV_TX_C); // one arrival per step and component (see the other branch)
-          if (c == 1 && step + 2 < n) issue_keys(step + 2);
-        }
-#endif
-        CLX_T(2 * c + 1);
+    for (u32 step = 0; step + 2 < n; step++) {
+      bar_sync(BAR_KEY, 256 + 32); // all product threads are through with this step's key tile
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // their reads of the buffer, before the async proxy overwrites it
+        issue_keys(step + 2);
       }
     }
     cluster_sync_all(); // a CTA must not exit while its peers may still push into its shared memory
-#ifdef BFHE_PHASE_TIMING
-    if (acc_dbg && lane == 0) // after the main warps' accumulator dump (they reach the cluster barrier after it)
-      for (int i = 0; i < 10; i++) {
-        acc_dbg[(gi * 2 + 1) * N + NB * k + 32 + 16 * 2 + i] = (u32)(tph[i] / 1000); // kilo-cycles
-        acc_dbg[(gi * 2 + 0) * N + NB * k + 32 + 16 * 2 + i] = tstamp[i];
-      }
-#endif
     return;
   }
 
@@ -346,20 +307,31 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
       }
   }
   // ---- per-thread constants, kept in registers for the whole blind rotation ----
-  const u32 ex = 2 * (__brev((u32)slot_position((int)k, tid)) >> (32 - LOGN)) + 1; // MAC slot tid evaluates at psi^ex
-  u32 fA[8], fAs[8], fB[8], fBs[8], fC[8], fCs[8], iS[5], iSs[5];
+  // product: group c computes component c at slots 2 gt and 2 gt + 1 (slot t evaluates at psi^ex(t))
+  const u32 ex0 = 2 * (__brev((u32)slot_position((int)k, 2 * gt)) >> (32 - LOGN)) + 1, ex1 = 2 * (__brev((u32)slot_position((int)k, 2 * gt + 1)) >> (32 - LOGN)) + 1;
+  u32 fA[8], fAs[8], fB[8], fBs[8], fC[8], fCs[8], iS[5][2], iSs[5][2];
 #pragma unroll
   for (int p = 0; p < 8; p++) { fA[p] = g_fw[p]; fAs[p] = g_fws[p]; }
   load8(g_fw + 8, fB, lane); load8(g_fws + 8, fBs, lane);
   load8(g_fw + 8 + 256, fC, lane); load8(g_fws + 8 + 256, fCs, lane);
 #pragma unroll
-  for (int s5 = 0; s5 < 5; s5++) { iS[s5] = g_iw[8 + 256 * s5 + tid]; iSs[s5] = g_iws[8 + 256 * s5 + tid]; }
+  for (int s5 = 0; s5 < 5; s5++) // inverse stage with half-size 2^s5 at my two slots (s5 = 0 pairs them: one twiddle, the upper slot's entry)
+#pragma unroll
+    for (int e = 0; e < 2; e++) { iS[s5][e] = g_iw[8 + 256 * s5 + 2 * gt + e]; iSs[s5][e] = g_iws[8 + 256 * s5 + 2 * gt + e]; }
+  const u32 iS5 = g_iw[4 + l], iS5s = g_iws[4 + l]; // half-size 32: one twiddle per 64 slots
   const u32 iw1 = P.itw[1], iw1s = P.itws[1], iwb = P.itw[2], iwbs = P.itws[2], iwc = P.itw[3], iwcs = P.itws[3];
   u32 iA[8], iAs[8]; // last three stages of the inverse sub-transform of block l (the row that CTA l sends)
 #pragma unroll
   for (int p = 0; p < 8; p++) { iA[p] = g_tw[(size_t)l * TWR + 2 * TWF + p]; iAs[p] = g_tw[(size_t)l * TWR + 2 * TWF + TWI + p]; }
   const int blk = lane >> 2, qq = lane & 3;
   const u32 dsh = (u32)(LOGBG * l); // my row's digit
+  u32 peer_mine[R - 1], peer_bar[R - 1]; // shared::cluster addresses in the three peers: my two words of this CTA's row of component c (parity 0), rbar[0][c]
+#pragma unroll
+  for (int p = 0; p < R - 1; p++) {
+    const u32 dest = (k + 1 + p) % R;
+    peer_mine[p] = dsmem_addr(rbuf + (size_t)(k * 2 + c) * NB + 2 * gt, dest);
+    peer_bar[p] = dsmem_addr(rbar + c, dest);
+  }
   cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
 
   for (u32 step = 0; step < n; step++) {
@@ -370,8 +342,8 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     // the key tile of this step was requested two steps ago: test its barrier once now (the ~100 cycles of a try_wait then overlap the
     // transform); the monomial factors do not depend on the transform either
     const bool key_in = mbar_test(kbar + par, (step >> 1) & 1);
-    const u32 mono = s_idx[step] * ex;
-    const u32 fp = s_F[f_index(mono)], fn = s_F[f_index(0u - mono)]; // (X^m - 1), (X^-m - 1) at this slot, Montgomery form
+    const u32 mono0 = s_idx[step] * ex0, mono1 = s_idx[step] * ex1; // (X^m - 1), (X^-m - 1) at my two slots, Montgomery form
+    const u32 fp[2] = {s_F[f_index(mono0)], s_F[f_index(mono1)]}, fn[2] = {s_F[f_index(0u - mono0)], s_F[f_index(0u - mono1)]};
     // ---- phase A: my group's accumulator words are published -> block k of the two cross-block forward stages of MY row, by look-up ----
     bar_sync(BAR_GROUP + c, 128);
     CLX_T(0);
@@ -409,66 +381,51 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     CLX_T(2);
     bar_sync(BAR_DCT, 256); // all eight rows of this step are in dct[par]
     CLX_T(3);
-    // ---- phase C: external product on my 256 slots, one slot per thread, component 0 first; the five inverse stages that stay inside a warp
-    //      (component 0's are independent of component 1's multiplications: the scheduler overlaps them); every finished value goes
-    //      straight into this CTA's row of the receive buffer ----
+    // ---- phase C: external product, group c computes component c: two adjacent slots per thread; then the six inverse stages that stay
+    //      inside a warp (the first inside the thread, five by shuffle, two independent values per stage); the finished values go straight
+    //      into this CTA's row of the receive buffer ----
     if (!key_in) mbar_wait(kbar + par, (step >> 1) & 1);
     CLX_T(4);
     {
-      u32 d[ROWS];
+      uint2 d[ROWS];
 #pragma unroll
-      for (int rw = 0; rw < ROWS; rw++) d[rw] = dct[(par * ROWS + rw) * NB + tid];
-      const uint4 *k4 = reinterpret_cast<const uint4 *>(s_key + (size_t)par * KEYPOLYS * NB) + tid; // quad g = (cc * 2 + sign) * 2 + half
-      u32 *mine = rbuf + (size_t)((par * R + k) * 2) * NB + tid;
-      auto mac = [&](int cc) -> u32 {
-        u64 s2[2] = {0, 0};
+      for (int rw = 0; rw < ROWS; rw++) d[rw] = *reinterpret_cast<const uint2 *>(dct + (par * ROWS + rw) * NB + 2 * gt);
+      // key tile: [quad g = (cc * 2 + sign) * 2 + half][slot parity e][gt][4 rows]
+      const uint4 *k4 = reinterpret_cast<const uint4 *>(s_key + (size_t)par * KEYPOLYS * NB) + (size_t)c * 4 * 2 * 128 + gt;
+      u64 s2[2][2] = {{0, 0}, {0, 0}}; // [slot parity][sign]
 #pragma unroll
-        for (int sg = 0; sg < 2; sg++)
+      for (int sg = 0; sg < 2; sg++)
 #pragma unroll
-          for (int hf = 0; hf < 2; hf++) {
-            const uint4 kv = k4[((cc * 2 + sg) * 2 + hf) * NB];
-            s2[sg] += (u64)d[4 * hf + 0] * kv.x;
-            s2[sg] += (u64)d[4 * hf + 1] * kv.y;
-            s2[sg] += (u64)d[4 * hf + 2] * kv.z;
-            s2[sg] += (u64)d[4 * hf + 3] * kv.w;
-          }
-        return redc((u64)redc(s2[0], Q, qinv) * fp + (u64)redc(s2[1], Q, qinv) * fn, Q, qinv); // < 2Q
-      };
-      using T0 = GsShfl1<2>; using T1 = GsShfl1<T0::OUTB>; using T2 = GsShfl1<T1::OUTB>; using T3 = GsShfl1<T2::OUTB>; using T4 = GsShfl1<T3::OUTB>;
-      static_assert(T4::OUTB == 4, "bound of the values handed to the last three inverse stages");
-      auto tail = [&](u32 t) -> u32 {
-        t = T0::run(t, iS[0], iSs[0], Q, 1, (lane & 1) != 0);
-        t = T1::run(t, iS[1], iSs[1], Q, 2, (lane & 2) != 0);
-        t = T2::run(t, iS[2], iSs[2], Q, 4, (lane & 4) != 0);
-        t = T3::run(t, iS[3], iSs[3], Q, 8, (lane & 8) != 0);
-        return T4::run(t, iS[4], iSs[4], Q, 16, (lane & 16) != 0);
-      };
-      u32 t0 = mac(0);
-      // component 0's shuffle stages, each followed by a quarter of component 1's multiplications (independent work in the shadow of the
-      // shuffle latency)
-      u64 s1[2] = {0, 0};
-      auto mac1_quarter = [&](int sg, int hf) {
-        const uint4 kv = k4[((1 * 2 + sg) * 2 + hf) * NB];
-        s1[sg] += (u64)d[4 * hf + 0] * kv.x;
-        s1[sg] += (u64)d[4 * hf + 1] * kv.y;
-        s1[sg] += (u64)d[4 * hf + 2] * kv.z;
-        s1[sg] += (u64)d[4 * hf + 3] * kv.w;
-      };
-      t0 = T0::run(t0, iS[0], iSs[0], Q, 1, (lane & 1) != 0);
-      mac1_quarter(0, 0);
-      t0 = T1::run(t0, iS[1], iSs[1], Q, 2, (lane & 2) != 0);
-      mac1_quarter(0, 1);
-      t0 = T2::run(t0, iS[2], iSs[2], Q, 4, (lane & 4) != 0);
-      mac1_quarter(1, 0);
-      t0 = T3::run(t0, iS[3], iSs[3], Q, 8, (lane & 8) != 0);
-      mac1_quarter(1, 1);
-      t0 = T4::run(t0, iS[4], iSs[4], Q, 16, (lane & 16) != 0);
-      mine[0] = t0;
-      bar_arrive(BAR_PROD + 0, 256 + 32); // the issue warp takes over
+        for (int hf = 0; hf < 2; hf++) {
+          const uint4 k0 = k4[((sg * 2 + hf) * 2 + 0) * 128], k1 = k4[((sg * 2 + hf) * 2 + 1) * 128];
+          s2[0][sg] += (u64)d[4 * hf + 0].x * k0.x; s2[1][sg] += (u64)d[4 * hf + 0].y * k1.x;
+          s2[0][sg] += (u64)d[4 * hf + 1].x * k0.y; s2[1][sg] += (u64)d[4 * hf + 1].y * k1.y;
+          s2[0][sg] += (u64)d[4 * hf + 2].x * k0.z; s2[1][sg] += (u64)d[4 * hf + 2].y * k1.z;
+          s2[0][sg] += (u64)d[4 * hf + 3].x * k0.w; s2[1][sg] += (u64)d[4 * hf + 3].y * k1.w;
+        }
+      u32 v0 = redc((u64)redc(s2[0][0], Q, qinv) * fp[0] + (u64)redc(s2[0][1], Q, qinv) * fn[0], Q, qinv); // < 2Q
+      u32 v1 = redc((u64)redc(s2[1][0], Q, qinv) * fp[1] + (u64)redc(s2[1][1], Q, qinv) * fn[1], Q, qinv);
       CLX_T(5);
-      const u32 v1 = redc((u64)redc(s1[0], Q, qinv) * fp + (u64)redc(s1[1], Q, qinv) * fn, Q, qinv); // < 2Q
-      mine[NB] = tail(v1);
-      bar_arrive(BAR_PROD + 1, 256 + 32);
+      { // half-size 1: my two slots are the pair (bound 2 -> 4)
+        const u32 df = v0 - v1 + 2 * Q;
+        v0 = v0 + v1;
+        v1 = mul_shoup(df, iS[0][1], iSs[0][1], Q);
+      }
+      using T1 = GsShfl1<4>; using T2 = GsShfl1<T1::OUTB>; using T3 = GsShfl1<T2::OUTB>; using T4 = GsShfl1<T3::OUTB>; using T5 = GsShfl1<T4::OUTB>;
+      static_assert(T5::OUTB <= 8, "bound of the values handed to the last two inverse stages");
+      v0 = T1::run(v0, iS[1][0], iSs[1][0], Q, 1, (lane & 1) != 0); v1 = T1::run(v1, iS[1][1], iSs[1][1], Q, 1, (lane & 1) != 0);
+      v0 = T2::run(v0, iS[2][0], iSs[2][0], Q, 2, (lane & 2) != 0); v1 = T2::run(v1, iS[2][1], iSs[2][1], Q, 2, (lane & 2) != 0);
+      v0 = T3::run(v0, iS[3][0], iSs[3][0], Q, 4, (lane & 4) != 0); v1 = T3::run(v1, iS[3][1], iSs[3][1], Q, 4, (lane & 4) != 0);
+      v0 = T4::run(v0, iS[4][0], iSs[4][0], Q, 8, (lane & 8) != 0); v1 = T4::run(v1, iS[4][1], iSs[4][1], Q, 8, (lane & 8) != 0);
+      v0 = T5::run(v0, iS5, iS5s, Q, 16, (lane & 16) != 0); v1 = T5::run(v1, iS5, iS5s, Q, 16, (lane & 16) != 0);
+#pragma unroll
+      for (int p = 0; p < R - 1; p++) st_async2(peer_mine[p] + par * (u32)(R * 2 * NB * 4), make_uint2(v0, v1), peer_bar[p] + 16u * par);
+      *reinterpret_cast<uint2 *>(rbuf + (size_t)((par * R + k) * 2 + c) * NB + 2 * gt) = make_uint2(v0, v1);
+      // 128 arrivals per step and component release the CTA's own row to group c; one of them also posts the bytes expected from the three
+      // peers (stores that landed earlier merely ran the count negative)
+      if (gt == 0) mbar_expect_tx(rbar + par * 2 + c, RECV_TX_C);
+      else mbar_arrive(rbar + par * 2 + c);
+      if (step + 2 < n) bar_arrive(BAR_KEY, 256 + 32); // the ninth warp may overwrite this step's key tile
     }
     CLX_T(6);
     // ---- phase E: my component's four partial rows have landed (mine stored above, the peers' by bulk copy).  Warp l of the group runs the
@@ -476,18 +433,19 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     //      stages for coefficients gt + 128 jj + 256 i1; accumulate; publish centred + offset ----
     mbar_wait(rbar + par * 2 + c, (step >> 1) & 1);
     CLX_T(7);
-    {
-      // (not in place: this CTA's own row is still the source of bulk copies that may be in flight)
+    { // (not in place: this CTA's own row is still the source of bulk copies that may be in flight)
       const u32 *rrow = rbuf + (size_t)((par * R + l) * 2 + c) * NB + lane;
       u32 *prow = pbuf + (size_t)(c * R + l) * NB + lane;
-      u32 x[8];
 #pragma unroll
-      for (int m = 0; m < 8; m++) x[m] = rrow[32 * m];
-      using S2 = Gs8<1, 4>; using S1 = Gs8<2, S2::OUTB>; using S0 = Gs8<4, S1::OUTB>;
-      S2::run(x, iA, iAs, Q); S1::run(x, iA, iAs, Q); S0::run(x, iA, iAs, Q);
-      static_assert(S0::OUTB <= 4, "partial values must stay below 4Q for the cross-block stages");
-#pragma unroll
-      for (int m = 0; m < 8; m++) prow[32 * m] = x[m];
+      for (int jj = 0; jj < 2; jj++) { // values t + 64 j, t = lane + 32 jj: half-size 64 (twiddle 2 + (j >> 1)), then half-size 128 (twiddle 1)
+        u32 x0 = rrow[32 * jj], x1 = rrow[32 * jj + 64], x2 = rrow[32 * jj + 128], x3 = rrow[32 * jj + 192]; // < 8Q
+        const u32 d01 = mul_shoup(x0 - x1 + 8 * Q, iA[2], iAs[2], Q), d23 = mul_shoup(x2 - x3 + 8 * Q, iA[3], iAs[3], Q); // < 2Q
+        const u32 s01 = x0 + x1, s23 = x2 + x3;                                                                          // < 16Q
+        prow[32 * jj] = lazy_reduce(s01 + s23, Q);                                                                       // < 2Q
+        prow[32 * jj + 128] = mul_shoup(s01 - s23 + 16 * Q, iA[1], iAs[1], Q);
+        prow[32 * jj + 64] = d01 + d23;                                                                                  // < 4Q
+        prow[32 * jj + 192] = mul_shoup(d01 - d23 + 2 * Q, iA[1], iAs[1], Q);
+      }
     }
     bar_sync(BAR_GROUP + c, 128);
     CLX_T(9);
@@ -545,14 +503,15 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   cluster_sync_all(); // a CTA must not exit while its peers may still push into its shared memory
 }
 
-// key copy of this kernel: [step][rank][quad g][slot t][4] <- evaluation-form key of kernels.cu ([chunk][lane][4] word order, slot P =
-// 32 lane + 4 chunk + r holds the evaluation at psi^(2 bitrev(P) + 1)).  Quad g = (cc * 2 + sign) * 2 + half holds rows 4 half .. 4 half + 3
-// of output component cc and key sign: one LDS.128 per quad in the product, and component 0's half of the tile is read first.
+// key copy of this kernel: [step][rank][quad g][slot parity e][gt][4] <- evaluation-form key of kernels.cu ([chunk][lane][4] word order, slot
+// P = 32 lane + 4 chunk + r holds the evaluation at psi^(2 bitrev(P) + 1)).  Quad g = (cc * 2 + sign) * 2 + half holds rows 4 half .. 4 half + 3
+// of output component cc and key sign at slot t = 2 gt + e: one conflict-free LDS.128 per quad and slot in the product.
 __global__ void bk_slice_clx_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t nsteps) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsteps * KEYPOLYS * N; i += (size_t)gridDim.x * blockDim.x) {
     const size_t step = i / ((size_t)KEYPOLYS * N), rem = i % ((size_t)KEYPOLYS * N);
-    const int rk = (int)(rem / ((size_t)KEYPOLYS * NB)), g = (int)((rem / (NB * 4)) % 8), t = (int)((rem / 4) % NB), e = (int)(rem % 4);
-    const int cc = g >> 2, sg = (g >> 1) & 1, hf = g & 1, rw = 4 * hf + e;
+    const int rk = (int)(rem / ((size_t)KEYPOLYS * NB)), g = (int)((rem / (NB * 4)) % 8), e = (int)((rem / (128 * 4)) % 2), gt = (int)((rem / 4) % 128),
+              w4 = (int)(rem % 4);
+    const int cc = g >> 2, sg = (g >> 1) & 1, hf = g & 1, rw = 4 * hf + w4, t = 2 * gt + e;
     const int pl = (sg * ROWS + rw) * 2 + cc; // polynomial index of kernels.cu's key: [sign][row][column]
     const int Ppos = slot_position(rk, t), sl = Ppos >> 5, j = Ppos & 31;
     dst[i] = src[(step * KEYPOLYS + pl) * N + ((j >> 2) * 32 + sl) * 4 + (j & 3)];

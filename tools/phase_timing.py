@@ -22,16 +22,16 @@ for count in [int(a) for a in os.environ.get('COUNTS', '1,148').split(',')]:
             print(count, "gates, comp", w, {n: round(float(v), 1) for n, v in zip(names, t[:, w].mean(0))}, "total kcyc", round(float(t[:, w].sum(1).mean()), 1))
         continue
     if os.environ.get('GPC') == '128':  # slot-sliced cluster kernel: [gate][component 1][256 rank + 32 + 16 * who + phase], who = main warp 0 / 1, push warp 0 / 1
-        names = ["group barrier", "A lut", "B sub-ntt", "dct barrier", "key wait", "C mac0+tail0+mac1", "C tail1", "recv wait", "E cross+acc", "E sub-intt+barrier"]
-        pnames = ["wait c0", "push c0", "wait c1", "push c1+key"] + ["-"] * 6
-        for who, label in enumerate(["main warp 0 (group 0)", "main warp 4 (group 1)", "issue warp"]):
+        names = ["group barrier", "A lut", "B sub-ntt", "dct barrier", "key wait", "C mac", "C inverse stages+push", "recv wait", "E cross+acc", "E sub-intt+barrier"]
+        pnames = ["wait", "push", "key"] + ["-"] * 7
+        for who, label in enumerate(["main warp 0 (group 0)", "main warp 4 (group 1)"]):
             t = np.stack([acc[:, 1, 256 * k + 32 + 16 * who:256 * k + 42 + 16 * who] for k in range(4)], 1).astype(np.float64)
             nm = names if who < 2 else pnames
             print(count, "gates,", label, {n: round(float(v), 1) for n, v in zip(nm, t.mean((0, 1))) if n != "-"}, "total kcyc", round(float(t.sum(2).mean()), 1))
         # one step's timeline (step 200, gate 0, CTA 0): clock of every mark relative to main warp 0 leaving the group barrier
-        st = [acc[0, 0, 32 + 16 * who:42 + 16 * who].astype(np.int64) for who in range(3)]
+        st = [acc[0, 0, 32 + 16 * who:42 + 16 * who].astype(np.int64) for who in range(2)]
         t0 = int(st[0][0])
-        for who, label in enumerate(["main 0", "main 4", "issue"]):
+        for who, label in enumerate(["main 0", "main 4"]):
             nm = names if who < 2 else pnames
             ev = sorted((int((v - t0) & 0xffffffff) if ((v - t0) & 0xffffffff) < 2**31 else int((v - t0) & 0xffffffff) - 2**32, n) for n, v in zip(nm, st[who]) if n != "-" and v)
             print("  timeline", label, " ".join("%s@%d" % (n.replace(" ", "_"), t) for t, n in ev))
