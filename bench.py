@@ -400,7 +400,8 @@ def aux_circuits(B, ctx, rank, world):
     vectors = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))
     res = {}
     cores = os.cpu_count() or 1
-    circuits = [("AES-non-expanded", "aes128", 2, 16), ("sha256", "sha256", 1, 100)]
+    # (name, key, repetitions -- the last one is reported; the first includes plan upload and graph capture --, CPU sampling stride)
+    circuits = [("AES-non-expanded", "aes128", 2, 16), ("sha256", "sha256", 2 if world > 1 else 1, 100)]
     if world == 1:
         circuits += [("md5", "md5", 1, 50), ("mult_32x32", "mult32", 2, 1), ("comparator_32bit_signed_lt", "cmp32", 2, 1)]
     for name, key, reps, every in circuits:
@@ -425,6 +426,7 @@ def aux_circuits(B, ctx, rank, world):
                         key + "_bootstraps": c.info()["bootstraps"], key + "_levels": c.info()["levels"],
                         key + "_waves": sch["n_levels"] - 1, key + "_waves_sharded": sch["n_sharded"], key + "_wave_cap": sch["wave_cap"]})
         res["launch_cost_ms_probe"] = sch["cost_ms"]
+        res["exchange"] = {0: "none (1 GPU)", 1: "ncclAllGather per sharded wave", 2: "key switch stores into every rank's slab (CUDA IPC + NVLink), flag per wave"}[c.exchange_mode()]
         if world > 1:  # every rank: same wire ciphertexts as an unsharded evaluation of the same schedule on this GPU
             mine = level_blocks_digest(c, c.download_slab())
             c1 = B.Circuit(ctx)

@@ -166,6 +166,11 @@ int bfhe_circuit_info(const bfhe_circuit *, uint32_t *n_inputs, uint32_t *input_
 /* multi-GPU: shard every level over world ranks; comm_id = 128-byte ncclUniqueId distributed by the caller */
 int bfhe_circuit_set_sharding(bfhe_circuit *, int rank, int world, const void *nccl_unique_id);
 int bfhe_get_nccl_unique_id(void *out128);
+/* how the ranks exchange a sharded level's output ciphertexts: 0 = single rank; 2 = the key-switch kernel stores every output into every
+ * rank's slab itself (peer slabs mapped with CUDA IPC, stores over NVLink, one flag per rank and level -- chosen when every rank could
+ * map every slab); 1 = one ncclAllGather per level (fallback, or BFHE_EXCHANGE=nccl in the environment).  Valid after the first
+ * encrypted SetInput. */
+int bfhe_circuit_exchange_mode(const bfhe_circuit *);
 /* schedule: 0 = the reference's ASAP waves (src/circuit.cpp:593-677), one launch per level; n > 0 = ready gates packed into
  * waves of at most n bootstraps by longest remaining path; -1 (default) = one gate per SM and rank when a device is attached,
  * ASAP otherwise.  Ciphertexts do not depend on the schedule.  bfhe_circuit_info always reports the ASAP statistics. */

@@ -57,6 +57,7 @@ ABI_SYMBOLS = [
     "bfhe_circuit_dump_gate_count", "bfhe_circuit_load_netlist", "bfhe_circuit_get_netlist", "bfhe_circuit_write_out",
     "bfhe_circuit_load_netlist_ex", "bfhe_circuit_set_shard_threshold", "bfhe_circuit_dump_gate_count_ex",
     "bfhe_circuit_dump_text", "bfhe_circuit_dff_plan", "bfhe_circuit_get_schedule",
+    "bfhe_circuit_exchange_mode",
     "bfhe_import_openfhe_json", "bfhe_export_openfhe_json", "bfhe_import_openfhe_ct_json", "bfhe_export_openfhe_ct_json",
 ]
 
@@ -134,6 +135,7 @@ def lib():
     L.bfhe_circuit_dump_text.argtypes = [vp, C.c_int, C.c_char_p, sz, C.POINTER(sz)]
     L.bfhe_circuit_dff_plan.argtypes = [vp, u32p, vp, sz]
     L.bfhe_circuit_get_schedule.argtypes = [vp, u32p, u32p, u32p, C.POINTER(C.c_double)]
+    L.bfhe_circuit_exchange_mode.argtypes = [vp]
     L.bfhe_import_openfhe_json.argtypes = [vp, C.c_int, C.c_char_p]
     L.bfhe_export_openfhe_json.argtypes = [vp, C.c_int, C.c_char_p]
     L.bfhe_import_openfhe_ct_json.argtypes = [vp, C.c_char_p, vp]
@@ -510,6 +512,10 @@ class Circuit:
     def set_sharding(self, rank, world, unique_id=None):
         self._ck(self.L.bfhe_circuit_set_sharding(self.h, rank, world, _ptr(unique_id)))
         self.world_size = world
+
+    def exchange_mode(self):
+        """0 = single rank, 1 = ncclAllGather per sharded level, 2 = fused into the key switch (stores into the peers' slabs)"""
+        return self.L.bfhe_circuit_exchange_mode(self.h)
 
     def use_graph(self, on):
         self._ck(self.L.bfhe_circuit_use_graph(self.h, int(on)))

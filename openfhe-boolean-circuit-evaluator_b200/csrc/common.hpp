@@ -85,8 +85,25 @@ int clx_fast_gates(); // up to this many gates the 4-CTA form runs all clusters 
 int launch_bk_slice_clx(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
 int launch_blind_rotate_clx(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
                             void *stream, LaunchInfo *info);
+// Multi-GPU exchange fused into the key switch: every output ciphertext is stored into every rank's wire slab (the peers'
+// slabs are mapped through CUDA IPC, the stores travel over NVLink), and the last CTA of the launch raises this rank's flag in every
+// peer's flag array.  Flag values only grow: value(epoch, index) = epoch * per_epoch + index + 1, `epoch` read from device memory so
+// that the launches can sit in a CUDA graph.  slabs == nullptr: single-GPU behaviour.
+struct PeerX {
+  u32 *const *slabs = nullptr; // [world] slab base of every rank as mapped HERE (own entry = local slab)
+  const u32 *local_base = nullptr;
+  u32 *const *flags = nullptr; // [world] flag array (u32[world]) of every rank as mapped here
+  u32 *counter = nullptr;      // local: CTAs of this launch that have finished their stores
+  const u32 *epoch = nullptr;  // local: Clock() count
+  u32 world = 1, rank = 0, index = 0, per_epoch = 1;
+};
 int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates, int count, const void *d_ksk,
-                     int ksk_elem_bytes, void *stream);
+                     int ksk_elem_bytes, void *stream, const PeerX *px = nullptr);
+// exchange plumbing (one tiny launch each): epoch += 1; wait until every peer's flag has reached value(epoch, index) -- index -1 = the
+// end-of-Clock signal of the previous epoch -- with a ~2 s timeout that sets *err instead of hanging; raise my flag at every peer
+int launch_peer_epoch_bump(u32 *epoch, void *stream);
+int launch_peer_wait(const u32 *local_flags, const u32 *epoch, u32 world, u32 rank, int index, u32 per_epoch, u32 *err, void *stream);
+int launch_peer_signal(const PeerX &px, void *stream);
 int launch_eval_not(const DevConst &P, const u32 *const *d_in, u32 *const *d_out, int count, void *stream);
 int launch_bk_convert(const DevConst &P, const u32 *d_coef, u32 *d_dev, size_t npoly, const u32 *d_twl, void *stream);
 int launch_dbg_ntt(const DevConst &P, const u32 *d_a, const u32 *d_b, u32 *d_rt, u32 *d_prod, int npoly, const u32 *d_twl,

@@ -1258,10 +1258,71 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
 // contiguous, 128-byte-aligned run.  PACK16: two uint16 residues per 32-bit lane load (qKS <= 2^16,
 // a power of two, so accumulating mod 2^32 per half and masking at the end is exact).
 // ------------------------------------------------------------------------------------------
+// ---- multi-GPU exchange fused into the key switch (PeerX, common.hpp) ----
+__device__ __forceinline__ void peer_store(const PeerX &px, const u32 *out, int k, u32 v) {
+  if (px.slabs == nullptr) return;
+  const size_t off = (size_t)(out - px.local_base) + (size_t)k;
+  for (u32 r = 0; r < px.world; r++)
+    if (r != px.rank) px.slabs[r][off] = v; // NVLink store into rank r's slab, same row
+}
+__device__ __forceinline__ void st_release_sys(u32 *p, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 ld_acquire_sys(const u32 *p) {
+  u32 v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// called by every thread of the CTAs that count (all threads of the CTA, convergent): the last of `total` CTAs raises the flags
+__device__ __forceinline__ void peer_publish(const PeerX &px, u32 total) {
+  if (px.slabs == nullptr) return;
+  __threadfence_system(); // my peer stores are performed system-wide before anything that follows
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const u32 done = atomicAdd(px.counter, 1u) + 1u;
+    if (done == total) {
+      atomicExch(px.counter, 0u); // next launch on this stream
+      __threadfence_system();
+      const u32 v = *px.epoch * px.per_epoch + px.index + 1u;
+      for (u32 r = 0; r < px.world; r++)
+        if (r != px.rank) st_release_sys(px.flags[r] + px.rank, v);
+    }
+  }
+}
+__global__ void peer_epoch_bump_kernel(u32 *epoch) { *epoch += 1; }
+__global__ void peer_wait_kernel(const u32 *flags, const u32 *epoch, u32 world, u32 rank, int index, u32 per_epoch, u32 *err) {
+  const u32 r = threadIdx.x;
+  if (r >= world || r == rank) return;
+  const u32 target = *epoch * per_epoch + (u32)(index + 1);
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(flags + r) - target) < 0) {
+    if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u + r); break; } // ~2 s: a peer died or the ranks disagree on the schedule
+    __nanosleep(200);
+  }
+}
+__global__ void peer_signal_kernel(const PeerX px) { // end-of-Clock signal: everything this rank did in the epoch is complete (stream order)
+  const u32 r = threadIdx.x;
+  if (r >= px.world || r == px.rank) return;
+  __threadfence_system();
+  st_release_sys(px.flags[r] + px.rank, *px.epoch * px.per_epoch + px.index + 1u);
+}
+int launch_peer_epoch_bump(u32 *epoch, void *stream) {
+  peer_epoch_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(epoch);
+  return (int)cudaGetLastError();
+}
+int launch_peer_wait(const u32 *local_flags, const u32 *epoch, u32 world, u32 rank, int index, u32 per_epoch, u32 *err, void *stream) {
+  if (world > 32) return (int)cudaErrorInvalidValue;
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(local_flags, epoch, world, rank, index, per_epoch, err);
+  return (int)cudaGetLastError();
+}
+int launch_peer_signal(const PeerX &px, void *stream) {
+  if (px.world > 32) return (int)cudaErrorInvalidValue;
+  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(px);
+  return (int)cudaGetLastError();
+}
+
 template <bool PACK16, int COLS, int RG>
 __global__ void __launch_bounds__(COLS *RG) keyswitch_kernel(const __grid_constant__ DevConst P, const u32 *__restrict__ ext,
                                                              const DevGate *__restrict__ gates, const void *__restrict__ ksk,
-                                                             int rowlen_words) {
+                                                             int rowlen_words, const PeerX px) {
   extern __shared__ u32 s_row[]; // N*dKS row ids, then RG*COLS*2 partial sums (u64 for !PACK16)
   const int N = P.N, dKS = P.dKS, nrows = N * dKS;
   const int tid = threadIdx.x, col = tid % COLS, rg = tid / COLS;
@@ -1309,9 +1370,12 @@ __global__ void __launch_bounds__(COLS *RG) keyswitch_kernel(const __grid_consta
       s %= qKS;
       const u64 base = (k == n) ? e[N] : 0; // out = (0, b) - sum of selected KSK rows
       const u64 v = (base + qKS - s) % qKS;
-      out[k] = (u32)(((2 * v * q + qKS) / (2 * qKS)) % q); // RoundqQ, exact integer form
+      const u32 res = (u32)(((2 * v * q + qKS) / (2 * qKS)) % q); // RoundqQ, exact integer form
+      out[k] = res;
+      peer_store(px, out, k, res);
     }
   }
+  peer_publish(px, gridDim.x);
 }
 
 // The same key switch on a 4-CTA cluster per gate (packed uint16 KSK only): each CTA gathers a quarter of the N*dKS rows, rank 0 adds the
@@ -1320,7 +1384,7 @@ __global__ void __launch_bounds__(COLS *RG) keyswitch_kernel(const __grid_consta
 template <int COLS, int RG>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(COLS *RG) keyswitch_cl4_kernel(const __grid_constant__ DevConst P, const u32 *__restrict__ ext,
                                                                                              const DevGate *__restrict__ gates,
-                                                                                             const void *__restrict__ ksk, int rowlen_words) {
+                                                                                             const void *__restrict__ ksk, int rowlen_words, const PeerX px) {
   __shared__ u32 s_row[512];               // row ids of this CTA's quarter
   __shared__ u32 s_part[RG * COLS * 2];    // per row group partial sums (lo, hi halves)
   __shared__ u32 s_tot[COLS * 2];          // this CTA's sums, read by rank 0
@@ -1376,9 +1440,12 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(COLS *RG) keyswitch_
       sum %= qKS;
       const u64 base = (k == n) ? e[N] : 0; // out = (0, b) - sum of selected KSK rows
       const u64 v = (base + qKS - sum) % qKS;
-      out[k] = (u32)(((2 * v * q + qKS) / (2 * qKS)) % q); // RoundqQ, exact integer form
+      const u32 res = (u32)(((2 * v * q + qKS) / (2 * qKS)) % q); // RoundqQ, exact integer form
+      out[k] = res;
+      peer_store(px, out, k, res);
     }
   }
+  if (rank == 0) peer_publish(px, gridDim.x >> 2); // one count per gate
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); // peers stay until rank 0 has read
 }
 
@@ -1388,8 +1455,9 @@ static int keyswitch_attrs() {
   return (int)cudaFuncSetAttribute(keyswitch_kernel<true, COLS, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
 }
 int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates, int count, const void *d_ksk, int elem_bytes,
-                     void *stream) {
+                     void *stream, const PeerX *pxp) {
   if (count <= 0) return 0;
+  const PeerX px = pxp ? *pxp : PeerX();
   cudaStream_t st = (cudaStream_t)stream;
   const int nrows = P.N * P.dKS;
   if (elem_bytes == 2) {
@@ -1404,15 +1472,15 @@ int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (nrows % 4 == 0 && nrows / 4 <= 512 && 4 * count <= sms)
-      keyswitch_cl4_kernel<COLS, RG><<<4 * count, COLS * RG, 0, st>>>(P, d_ext, d_gates, d_ksk, rowlen_words);
+      keyswitch_cl4_kernel<COLS, RG><<<4 * count, COLS * RG, 0, st>>>(P, d_ext, d_gates, d_ksk, rowlen_words, px);
     else
-      keyswitch_kernel<true, COLS, RG><<<count, COLS * RG, smem, st>>>(P, d_ext, d_gates, d_ksk, rowlen_words);
+      keyswitch_kernel<true, COLS, RG><<<count, COLS * RG, smem, st>>>(P, d_ext, d_gates, d_ksk, rowlen_words, px);
   } else {
     constexpr int COLS = 128, RG = 4;
     const int rowlen_words = P.ct_stride;
     if (rowlen_words > COLS) return (int)cudaErrorInvalidValue;
     size_t smem = (size_t)((nrows + 1) & ~1) * 4 + (size_t)RG * COLS * 2 * 8;
-    keyswitch_kernel<false, COLS, RG><<<count, COLS * RG, smem, st>>>(P, d_ext, d_gates, d_ksk, rowlen_words);
+    keyswitch_kernel<false, COLS, RG><<<count, COLS * RG, smem, st>>>(P, d_ext, d_gates, d_ksk, rowlen_words, px);
   }
   return (int)cudaGetLastError();
 }

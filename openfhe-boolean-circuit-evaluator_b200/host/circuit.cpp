@@ -10,12 +10,14 @@
 // (circuit outputs, verify mode).
 //
 // Multi-GPU: every level's gate list is block-partitioned over the ranks, keys and the wire slab are
-// replicated, and the level's output rows are exchanged with one in-place ncclAllGather.
+// replicated, and the level's output rows are exchanged -- by the key-switch kernel itself, which stores every output into every rank's
+// slab over NVLink (setup_peer_exchange), or with one in-place ncclAllGather where the slabs cannot be mapped.
 #include "../csrc/engine.hpp"
 #include "netlist.hpp"
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <queue>
@@ -65,7 +67,14 @@ struct Level {
 };
 // launch costs (ms) of one blind rotation + key switch per kernel form; measured once per context by probe_costs(), else these
 // B200 defaults.  In sharded runs the ranks agree on the element-wise maximum, so that every rank builds the same schedule.
-struct FormCosts { double cl4 = 1.30, cl2 = 1.55, lat = 2.36, thr = 7.6, exchange = 0.05; bool measured = false; };
+// exchange: what a sharded level pays on top of its kernels -- the key switch's peer stores, one flag round trip over NVLink and one
+// tiny wait launch (~0.015 ms), or one ncclAllGather (~0.05 ms, BFHE_EXCHANGE=nccl).  The plan is made before the slabs exist, so the
+// peer-store figure is assumed unless NCCL was asked for; should the mapping fail later, the plan is merely a little optimistic.
+struct FormCosts {
+  double cl4 = 1.05, cl2 = 1.55, lat = 2.36, thr = 7.6, exchange = exchange_default();
+  bool measured = false;
+  static double exchange_default() { const char *m = std::getenv("BFHE_EXCHANGE"); return m && std::strcmp(m, "nccl") == 0 ? 0.05 : 0.015; }
+};
 inline bool is_single(GateKind k) {
   return k == GateKind::AND || k == GateKind::OR || k == GateKind::NAND || k == GateKind::NOR || k == GateKind::XOR_FAST || k == GateKind::XNOR_FAST;
 }
@@ -130,6 +139,14 @@ struct bfhe_circuit {
   bool dev_ready = false;
   cudaGraphExec_t graph = nullptr;
   bool use_graph = true;
+  // multi-GPU exchange by direct stores into the peers' slabs (PeerX, csrc/common.hpp); falls back to ncclAllGather when the slabs
+  // cannot be mapped (no peer access) or BFHE_EXCHANGE=nccl
+  bool peer_ok = false;
+  std::vector<void *> peer_slab_map, peer_flag_map; // cudaIpcOpenMemHandle results (null for the own rank)
+  u32 **d_peer_slabs = nullptr, **d_peer_flags = nullptr;
+  u32 *x_flags = nullptr, *x_counter = nullptr, *x_epoch = nullptr, *x_err = nullptr; // one allocation: flags[32] | counter | epoch | err
+  uint32_t x_per_epoch = 1;
+  std::vector<int> shard_index; // level -> index among the sharded levels (-1: not exchanged)
 
   // values
   std::vector<uint8_t> in_bits_set, plain_wire;
@@ -143,8 +160,14 @@ static void free_device(bfhe_circuit *c) {
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
     if (c->graph) cudaGraphExecDestroy(c->graph);
+    for (void *m : c->peer_slab_map) if (m) cudaIpcCloseMemHandle(m);
+    for (void *m : c->peer_flag_map) if (m) cudaIpcCloseMemHandle(m);
+    cudaFree(c->d_peer_slabs); cudaFree(c->d_peer_flags); cudaFree(c->x_flags);
     cudaFree(c->slab); cudaFree(c->d_desc); cudaFree(c->d_not_in); cudaFree(c->d_not_out); cudaFree(c->d_ext);
   }
+  c->peer_slab_map.clear(); c->peer_flag_map.clear();
+  c->d_peer_slabs = nullptr; c->d_peer_flags = nullptr; c->x_flags = c->x_counter = c->x_epoch = c->x_err = nullptr;
+  c->peer_ok = false;
   c->graph = nullptr; c->slab = nullptr; c->d_desc = nullptr; c->d_not_in = nullptr; c->d_not_out = nullptr; c->d_ext = nullptr;
   c->dev_ready = false;
 }
@@ -623,6 +646,76 @@ static int probe_costs(bfhe_circuit *c) {
   return BFHE_OK;
 }
 
+// Map every peer's wire slab and flag array into this process (CUDA IPC) so that the key switch can store its outputs into all slabs
+// directly.  The 64-byte handles travel through one ncclAllGather, which is also the barrier that orders "flags initialised" before
+// "anybody signals".  Every rank takes the same decision (the allgathered record carries an ok byte): peer stores or ncclAllGather.
+static int setup_peer_exchange(bfhe_circuit *c) {
+  bfhe_ctx *x = c->ctx;
+  const int W = c->world;
+  c->shard_index.assign(c->levels.size(), -1);
+  uint32_t S = 0;
+  for (size_t L = 0; L < c->levels.size(); L++)
+    if (c->level_rpr[L] && c->levels[L].sharded) c->shard_index[L] = (int)S++;
+  c->x_per_epoch = S + 1;
+  if (W <= 1 || W > 32 || !c->comm) return BFHE_OK;
+  const char *mode = std::getenv("BFHE_EXCHANGE");
+  struct Rec { cudaIpcMemHandle_t slab, flags; uint32_t ok; uint32_t pad[3]; };
+  static_assert(sizeof(Rec) % 16 == 0, "record size");
+  Rec mine{};
+  BFHE_CUDA(cudaMalloc(&c->x_flags, 64 * sizeof(u32)));
+  c->x_counter = c->x_flags + 32; c->x_epoch = c->x_flags + 33; c->x_err = c->x_flags + 34;
+  {
+    std::vector<u32> init(64, 0);
+    for (int r = 0; r < 32; r++) init[r] = c->x_per_epoch; // = value(epoch 0, end-of-Clock): the first Clock's opening wait passes
+    BFHE_CUDA(cudaMemcpy(c->x_flags, init.data(), init.size() * sizeof(u32), cudaMemcpyHostToDevice));
+  }
+  mine.ok = !(mode && std::strcmp(mode, "nccl") == 0) && cudaIpcGetMemHandle(&mine.slab, c->slab) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine.flags, c->x_flags) == cudaSuccess;
+  cudaGetLastError();
+  Rec *d = nullptr;
+  BFHE_CUDA(cudaMalloc(&d, (size_t)W * sizeof(Rec)));
+  BFHE_CUDA(cudaMemcpyAsync(d + c->rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice, x->stream));
+  int nrc = g_nccl.AllGather(d + c->rank, d, sizeof(Rec) / 4, NCCL_UINT32, c->comm, x->stream);
+  if (nrc) { cudaFree(d); set_error("ncclAllGather (IPC handles) failed"); return BFHE_ERR_NCCL; }
+  std::vector<Rec> all(W);
+  BFHE_CUDA(cudaMemcpyAsync(all.data(), d, (size_t)W * sizeof(Rec), cudaMemcpyDeviceToHost, x->stream));
+  BFHE_CUDA(cudaStreamSynchronize(x->stream));
+  bool ok = true;
+  for (int r = 0; r < W; r++) ok = ok && all[r].ok;
+  std::vector<u32 *> slabs(W, nullptr), flags(W, nullptr);
+  c->peer_slab_map.assign(W, nullptr); c->peer_flag_map.assign(W, nullptr);
+  uint32_t opened = ok ? 1 : 0;
+  for (int r = 0; r < W && opened; r++) {
+    if (r == c->rank) { slabs[r] = c->slab; flags[r] = c->x_flags; continue; }
+    if (cudaIpcOpenMemHandle(&c->peer_slab_map[r], all[r].slab, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&c->peer_flag_map[r], all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; break; }
+    slabs[r] = (u32 *)c->peer_slab_map[r]; flags[r] = (u32 *)c->peer_flag_map[r];
+  }
+  // second round: did EVERY rank manage to open every mapping?  (also the barrier after which signalling may start)
+  uint32_t *dflag = reinterpret_cast<uint32_t *>(d);
+  BFHE_CUDA(cudaMemcpyAsync(dflag + c->rank, &opened, sizeof(uint32_t), cudaMemcpyHostToDevice, x->stream));
+  nrc = g_nccl.AllGather(dflag + c->rank, dflag, 1, NCCL_UINT32, c->comm, x->stream);
+  if (nrc) { cudaFree(d); set_error("ncclAllGather (IPC status) failed"); return BFHE_ERR_NCCL; }
+  std::vector<uint32_t> st(W);
+  BFHE_CUDA(cudaMemcpyAsync(st.data(), dflag, (size_t)W * sizeof(uint32_t), cudaMemcpyDeviceToHost, x->stream));
+  BFHE_CUDA(cudaStreamSynchronize(x->stream));
+  cudaFree(d);
+  for (int r = 0; r < W; r++) ok = ok && st[r];
+  if (!ok) return BFHE_OK; // ncclAllGather path
+  BFHE_CUDA(cudaMalloc(&c->d_peer_slabs, (size_t)W * sizeof(u32 *)));
+  BFHE_CUDA(cudaMalloc(&c->d_peer_flags, (size_t)W * sizeof(u32 *)));
+  BFHE_CUDA(cudaMemcpy(c->d_peer_slabs, slabs.data(), (size_t)W * sizeof(u32 *), cudaMemcpyHostToDevice));
+  BFHE_CUDA(cudaMemcpy(c->d_peer_flags, flags.data(), (size_t)W * sizeof(u32 *), cudaMemcpyHostToDevice));
+  c->peer_ok = true;
+  return BFHE_OK;
+}
+static PeerX peer_x(const bfhe_circuit *c, uint32_t index) {
+  PeerX px;
+  px.slabs = c->d_peer_slabs; px.local_base = c->slab; px.flags = c->d_peer_flags; px.counter = c->x_counter; px.epoch = c->x_epoch;
+  px.world = (u32)c->world; px.rank = (u32)c->rank; px.index = index; px.per_epoch = c->x_per_epoch;
+  return px;
+}
+
 static int upload_plan(bfhe_circuit *c) {
   bfhe_ctx *x = c->ctx;
   if (x->device < 0) { set_error("no CUDA device attached (this engine has no CPU fallback)"); return BFHE_ERR_CUDA; }
@@ -677,6 +770,8 @@ static int upload_plan(bfhe_circuit *c) {
   BFHE_CUDA(cudaMemcpy(c->d_not_out, nout.data(), nout.size() * sizeof(void *), cudaMemcpyHostToDevice));
   c->ext_cap = widest;
   BFHE_CUDA(cudaMalloc(&c->d_ext, (size_t)widest * (x->p.N + 4) * 4));
+  rc = setup_peer_exchange(c);
+  if (rc) return rc;
   c->dev_ready = true;
   return BFHE_OK;
 }
@@ -686,6 +781,12 @@ static int enqueue_levels(bfhe_circuit *c) {
   bfhe_ctx *x = c->ctx;
   const size_t st = x->p.ct_stride;
   const size_t NLv = c->levels.size();
+  const bool px_on = c->world > 1 && c->peer_ok;
+  if (px_on) { // new epoch; nobody stores into a peer's slab before that peer has finished its previous Clock (its end-of-Clock signal)
+    int rc = launch_peer_epoch_bump(c->x_epoch, x->stream);
+    if (!rc) rc = launch_peer_wait(c->x_flags, c->x_epoch, (u32)c->world, (u32)c->rank, -1, c->x_per_epoch, c->x_err, x->stream);
+    if (rc) return cuda_fail((cudaError_t)rc, "peer exchange launch");
+  }
   if (c->n_dff) { // clocked circuits: the state rows take the values latched at the end of the previous clock (or the power-up values)
     int rc = launch_eval_not(x->P, c->d_not_in + c->not_off[NLv + 1], c->d_not_out + c->not_off[NLv + 1], (int)c->n_dff, x->stream);
     if (rc) return cuda_fail((cudaError_t)rc, "DFF state launch");
@@ -696,10 +797,17 @@ static int enqueue_levels(bfhe_circuit *c) {
       int rc = launch_blind_rotate(x->P, x->p.method == BFHE_AP, c->d_desc + c->desc_off[L], (int)n, x->d_bk, x->d_twl, x->d_psiM,
                                    c->d_ext, nullptr, x->force_g, x->stream, nullptr, &x->v2);
       if (rc) return cuda_fail((cudaError_t)rc, "blind_rotate launch");
-      rc = launch_keyswitch(x->P, c->d_ext, c->d_desc + c->desc_off[L], (int)n, x->d_ksk, x->ksk_elem_bytes, x->stream);
+      const bool xl = px_on && c->shard_index[L] >= 0;
+      const PeerX px = xl ? peer_x(c, (uint32_t)c->shard_index[L]) : PeerX();
+      rc = launch_keyswitch(x->P, c->d_ext, c->d_desc + c->desc_off[L], (int)n, x->d_ksk, x->ksk_elem_bytes, x->stream, xl ? &px : nullptr);
       if (rc) return cuda_fail((cudaError_t)rc, "keyswitch launch");
     }
-    if (c->world > 1 && c->level_rpr[L] && c->levels[L].sharded) {
+    if (px_on && c->shard_index[L] >= 0) { // outputs were stored into every slab by the key switch: wait for the peers' flags of this level
+      int rc = 0;
+      if (!n) rc = launch_peer_signal(peer_x(c, (uint32_t)c->shard_index[L]), x->stream); // nothing of this level is mine: only say so
+      if (!rc) rc = launch_peer_wait(c->x_flags, c->x_epoch, (u32)c->world, (u32)c->rank, c->shard_index[L], c->x_per_epoch, c->x_err, x->stream);
+      if (rc) return cuda_fail((cudaError_t)rc, "peer exchange launch");
+    } else if (c->world > 1 && c->level_rpr[L] && c->levels[L].sharded) {
       u32 *base = c->slab + (size_t)c->levels[L].first_row * st;
       const size_t cnt = (size_t)c->level_rpr[L] * st;
       int nrc = g_nccl.AllGather(base + (size_t)c->rank * cnt, base, cnt, NCCL_UINT32, c->comm, x->stream);
@@ -715,6 +823,10 @@ static int enqueue_levels(bfhe_circuit *c) {
                   // mode read consistent values, and a D that is another flip-flop's Q sees the old state)
     int rc = launch_eval_not(x->P, c->d_not_in + c->not_off[NLv], c->d_not_out + c->not_off[NLv], (int)c->n_dff, x->stream);
     if (rc) return cuda_fail((cudaError_t)rc, "DFF latch launch");
+  }
+  if (px_on) { // end-of-Clock signal: this rank no longer reads its slab, the peers may start storing the next Clock's rows
+    int rc = launch_peer_signal(peer_x(c, c->x_per_epoch - 1), x->stream);
+    if (rc) return cuda_fail((cudaError_t)rc, "peer exchange launch");
   }
   return BFHE_OK;
 }
@@ -972,6 +1084,11 @@ extern "C" int bfhe_circuit_set_shard_threshold(bfhe_circuit *c, int min_bootstr
   return BFHE_OK;
 }
 /* the schedule the planner chose: wave capacity (0 = ASAP levels), number of levels incl. the input level, how many of them are sharded */
+extern "C" int bfhe_circuit_exchange_mode(const bfhe_circuit *c) {
+  if (!c) return BFHE_ERR_ARG;
+  if (c->world <= 1) return 0;
+  return c->dev_ready && c->peer_ok ? 2 : 1;
+}
 extern "C" int bfhe_circuit_get_schedule(const bfhe_circuit *c, uint32_t *wave_cap, uint32_t *n_levels, uint32_t *n_sharded, double *cost_ms4) {
   if (!c || !c->planned) return BFHE_ERR_STATE;
   if (wave_cap) *wave_cap = c->wave_cap;
@@ -1132,14 +1249,14 @@ extern "C" int bfhe_circuit_clock(bfhe_circuit *c, uint8_t *out_bits, size_t cap
     BFHE_CUDA(cudaEventCreate(&e1));
     int rc = BFHE_OK;
     if (c->use_graph && !c->graph) { // one CUDA graph per circuit, sharded or not (NCCL collectives are capturable)
-      if (c->world > 1) { // NCCL's lazy set-up (channels, buffers) must happen outside the capture: one eager exchange first
+      if (c->world > 1 && !c->peer_ok) { // NCCL's lazy set-up (channels, buffers) must happen outside the capture: one eager exchange first
         int nrc = g_nccl.AllGather(c->slab + (size_t)c->rank * st, c->slab, st, NCCL_UINT32, c->comm, x->stream);
         if (nrc) { set_error("ncclAllGather warm-up failed"); return BFHE_ERR_NCCL; }
         BFHE_CUDA(cudaStreamSynchronize(x->stream));
         // rows 0 .. world-1 (level-0 outputs) were overwritten with copies of themselves per rank: level 0 rewrites them
       }
       cudaGraph_t g = nullptr;
-      BFHE_CUDA(cudaStreamBeginCapture(x->stream, c->world > 1 ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
+      BFHE_CUDA(cudaStreamBeginCapture(x->stream, c->world > 1 && !c->peer_ok ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
       rc = enqueue_levels(c);
       cudaError_t ce = cudaStreamEndCapture(x->stream, &g);
       if (rc) { if (g) cudaGraphDestroy(g); return rc; }
@@ -1162,6 +1279,11 @@ extern "C" int bfhe_circuit_clock(bfhe_circuit *c, uint8_t *out_bits, size_t cap
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     c->device_ms += ms;
+    if (c->world > 1 && c->peer_ok) { // a wait for a peer's flag timed out (the kernels do not hang: they record which peer and go on)
+      u32 xe = 0;
+      BFHE_CUDA(cudaMemcpy(&xe, c->x_err, sizeof xe, cudaMemcpyDeviceToHost));
+      if (xe) { set_error("multi-GPU exchange: no signal from rank " + std::to_string(xe - 1) + " within 2 s (rank lost, or the ranks disagree on the schedule)"); return BFHE_ERR_NCCL; }
+    }
     // OUTPUT gates: decrypt on the host (src/circuit.cpp:796-801)
     std::vector<u32> rows;
     if (c->verify) {
