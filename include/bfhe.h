@@ -163,7 +163,9 @@ int bfhe_circuit_write_out(const bfhe_circuit *, const char *path);
 int bfhe_circuit_set_flags(bfhe_circuit *, int plaintext, int encrypted, int verify); /* setPlaintext/Encrypted/Verify */
 int bfhe_circuit_info(const bfhe_circuit *, uint32_t *n_inputs, uint32_t *input_bits /*[8]*/, uint32_t *n_output_bits,
                       uint32_t *n_gates, uint32_t *n_bootstraps, uint32_t *n_levels, uint32_t *max_width);
-/* multi-GPU: shard every level over world ranks; comm_id = 128-byte ncclUniqueId distributed by the caller */
+/* multi-GPU: shard every level over world ranks; comm_id = 128-byte ncclUniqueId distributed by the caller.  From here on set_sharding,
+ * set_wave_capacity, set_shard_threshold, set_flags, set_input and clock are COLLECTIVE: every rank makes the same calls in the same order
+ * (they exchange launch costs and memory handles, and a rank's Clock stores into its peers' slabs) */
 int bfhe_circuit_set_sharding(bfhe_circuit *, int rank, int world, const void *nccl_unique_id);
 int bfhe_get_nccl_unique_id(void *out128);
 /* how the ranks exchange a sharded level's output ciphertexts: 0 = single rank; 2 = the key-switch kernel stores every output into every

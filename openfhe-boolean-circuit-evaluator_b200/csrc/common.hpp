@@ -100,7 +100,7 @@ struct PeerX {
 int launch_keyswitch(const DevConst &P, const u32 *d_ext, const DevGate *d_gates, int count, const void *d_ksk,
                      int ksk_elem_bytes, void *stream, const PeerX *px = nullptr);
 // exchange plumbing (one tiny launch each): epoch += 1; wait until every peer's flag has reached value(epoch, index) -- index -1 = the
-// end-of-Clock signal of the previous epoch -- with a ~2 s timeout that sets *err instead of hanging; raise my flag at every peer
+// end-of-Clock signal of the previous epoch -- with a timeout (30 s, BFHE_EXCHANGE_TIMEOUT_S) that sets *err instead of hanging; raise my flag at every peer
 int launch_peer_epoch_bump(u32 *epoch, void *stream);
 int launch_peer_wait(const u32 *local_flags, const u32 *epoch, u32 world, u32 rank, int index, u32 per_epoch, u32 *err, void *stream);
 int launch_peer_signal(const PeerX &px, void *stream);

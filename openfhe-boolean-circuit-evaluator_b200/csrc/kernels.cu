@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <type_traits>
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 namespace bfhe {
 
@@ -1288,13 +1289,13 @@ __device__ __forceinline__ void peer_publish(const PeerX &px, u32 total) {
   }
 }
 __global__ void peer_epoch_bump_kernel(u32 *epoch) { *epoch += 1; }
-__global__ void peer_wait_kernel(const u32 *flags, const u32 *epoch, u32 world, u32 rank, int index, u32 per_epoch, u32 *err) {
+__global__ void peer_wait_kernel(const u32 *flags, const u32 *epoch, u32 world, u32 rank, int index, u32 per_epoch, u32 *err, long long timeout_cycles) {
   const u32 r = threadIdx.x;
   if (r >= world || r == rank) return;
   const u32 target = *epoch * per_epoch + (u32)(index + 1);
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(flags + r) - target) < 0) {
-    if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u + r); break; } // ~2 s: a peer died or the ranks disagree on the schedule
+    if (clock64() - t0 > timeout_cycles) { atomicExch(err, 1u + r); break; } // a peer died or the ranks disagree on the schedule
     __nanosleep(200);
   }
 }
@@ -1310,7 +1311,14 @@ int launch_peer_epoch_bump(u32 *epoch, void *stream) {
 }
 int launch_peer_wait(const u32 *local_flags, const u32 *epoch, u32 world, u32 rank, int index, u32 per_epoch, u32 *err, void *stream) {
   if (world > 32) return (int)cudaErrorInvalidValue;
-  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(local_flags, epoch, world, rank, index, per_epoch, err);
+  // A rank may legitimately lag by seconds (host-side verify of a large circuit between two Clocks, graph instantiation): the limit only
+  // has to turn a dead peer into an error instead of a hung GPU.  BFHE_EXCHANGE_TIMEOUT_S overrides the 30 s default.
+  static const long long cycles = [] {
+    const char *e = std::getenv("BFHE_EXCHANGE_TIMEOUT_S");
+    const double sec = e && std::atof(e) > 0 ? std::atof(e) : 30.0;
+    return (long long)(sec * 2.0e9);
+  }();
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(local_flags, epoch, world, rank, index, per_epoch, err, cycles);
   return (int)cudaGetLastError();
 }
 int launch_peer_signal(const PeerX &px, void *stream) {

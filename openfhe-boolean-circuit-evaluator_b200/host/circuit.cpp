@@ -1282,7 +1282,7 @@ extern "C" int bfhe_circuit_clock(bfhe_circuit *c, uint8_t *out_bits, size_t cap
     if (c->world > 1 && c->peer_ok) { // a wait for a peer's flag timed out (the kernels do not hang: they record which peer and go on)
       u32 xe = 0;
       BFHE_CUDA(cudaMemcpy(&xe, c->x_err, sizeof xe, cudaMemcpyDeviceToHost));
-      if (xe) { set_error("multi-GPU exchange: no signal from rank " + std::to_string(xe - 1) + " within 2 s (rank lost, or the ranks disagree on the schedule)"); return BFHE_ERR_NCCL; }
+      if (xe) { set_error("multi-GPU exchange: no signal from rank " + std::to_string(xe - 1) + " within the exchange timeout (rank lost, or the ranks disagree on the schedule)"); return BFHE_ERR_NCCL; }
     }
     // OUTPUT gates: decrypt on the host (src/circuit.cpp:796-801)
     std::vector<u32> rows;
