@@ -1386,6 +1386,10 @@ __global__ void __launch_bounds__(COLS *RG) keyswitch_kernel(const __grid_consta
   peer_publish(px, gridDim.x);
 }
 
+#ifndef KS_CL4_UNROLL
+#define KS_CL4_UNROLL 16 // measured 8: 29.2 us, 16: 27.1 us, 32: 35.1 us per 33-gate wave
+#endif
+constexpr int ks_cl4_unroll = KS_CL4_UNROLL; // row gathers in flight per thread
 // The same key switch on a 4-CTA cluster per gate (packed uint16 KSK only): each CTA gathers a quarter of the N*dKS rows, rank 0 adds the
 // four partial sums out of its peers' shared memory (DSMEM) and finishes.  The one-CTA form is latency-bound (512 dependent row
 // gathers per thread, 55 us whatever the batch); narrow circuit waves (1.2 - 1.5 ms each) pay that every wave.
@@ -1412,7 +1416,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(COLS *RG) keyswitch_
   const u32 *k32 = reinterpret_cast<const u32 *>(ksk);
   u32 lo = 0, hi = 0;
   if (col < rowlen_words) {
-#pragma unroll 8
+#pragma unroll ks_cl4_unroll
     for (int r = rg; r < quarter; r += RG) {
       const u32 w = __ldg(k32 + (size_t)s_row[r] * rowlen_words + col);
       lo += w & 0xffffu;
