@@ -552,7 +552,27 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
     PT_T(0);
     // GINX: this warp's first key chunk is requested BEFORE the barrier, so the L2 round trip overlaps the wait for
     // the slower warps of the CTA instead of stalling the external product (ncu r1: 6 % of samples sat on these loads)
-    uint4 kr[AP ? 1 : 2][ROWS][LEAN ? 1 : 2];
+    // AP: every gate has its own key (BK[i][digit][k]), so nothing is shared between the gates of the CTA; the two halves of kr[] are a
+    // double buffer instead -- gate j's words are requested while gate j - 1 is multiplied (the first two before the barrier), which takes
+    // the L2 round trip of 16 LDG.128 per gate and step off the critical path
+    uint4 kr[2][ROWS][LEAN ? 1 : 2];
+    constexpr int JN = (G + GS - 1) / GS; // gates per item
+    auto ap_key = [&](int gg, int qc) -> const u32 * { // this step's key of gate gg at chunk qc (no such gate, or digit 0 = step skipped: any
+      const u32 a0 = gg < gcount ? s_idx[gg * NPAD + step] : 0u; // valid key, the words are loaded and not used -- unconditional loads keep kr[] in registers)
+      const u32 i = step / P.dR, k = step % P.dR;
+      return bk + (((size_t)i * (P.baseR - 1) + (a0 ? a0 - 1 : 0u)) * P.dR + k) * (ROWS * 2) * N + (qc * 32 + lane) * 4;
+    };
+#define BFHE_AP_LOAD(buf, kb)                                                                                          \
+  do {                                                                                                                 \
+    const u32 *kb_ = (kb);                                                                                             \
+    _Pragma("unroll") for (int r = 0; r < ROWS; r++)                                                                   \
+      _Pragma("unroll") for (int cc = 0; cc < (LEAN ? 1 : 2); cc++)                                                    \
+        kr[buf][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb_ + (size_t)(r * 2 + cc) * N));                        \
+  } while (0)
+    if (AP && !LEAN && warp < C * GS) {
+      BFHE_AP_LOAD(0, ap_key(warp / C, warp % C));
+      if (JN > 1) BFHE_AP_LOAD(1, ap_key(warp / C + GS, warp % C));
+    }
     if (!AP && warp < C * GS) {
       const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + ((warp % C) * 32 + lane) * 4;
 #pragma unroll
@@ -642,17 +662,22 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
 #pragma unroll
       for (int r = 0; r < 4; r++) eB[r] = 2 * ((brev(r, 2) << (LOGN - 2)) | (brev(qc, LOGN - 7) << 5));
 
-      for (int gg = gs0; gg < gcount; gg += GS) {
+      if (AP && item != warp) { // further chunks of this warp: no prefetch across items
+        BFHE_AP_LOAD(0, ap_key(gs0, qc));
+        if (JN > 1) BFHE_AP_LOAD(1, ap_key(gs0 + GS, qc));
+      }
+#pragma unroll
+      for (int j = 0; j < JN; j++) {
+        const int gg = gs0 + j * GS;
+        constexpr int KB0 = 0; // (silences unused warnings when AP is false)
+        (void)KB0;
+        const bool ap_active = AP && gg < gcount && s_idx[(gg < gcount ? gg : 0) * NPAD + step] != 0;
+        if (gg >= gcount || (AP && !ap_active)) { // nothing to multiply for this gate in this step; keep the double buffer moving
+          if (AP && j + 2 < JN) { if ((j & 1) == 0) BFHE_AP_LOAD(0, ap_key(gs0 + (j + 2) * GS, qc)); else BFHE_AP_LOAD(1, ap_key(gs0 + (j + 2) * GS, qc)); }
+          continue;
+        }
         u32 fp[4], fn[4];
         if (AP) {
-          const u32 a0 = s_idx[gg * NPAD + step];
-          if (a0 == 0) continue;
-          const u32 i = step / P.dR, k = step % P.dR;
-          const u32 *kb = bk + (((size_t)i * (P.baseR - 1) + (a0 - 1)) * P.dR + k) * (ROWS * 2) * N + (qc * 32 + lane) * 4;
-#pragma unroll
-          for (int r = 0; r < ROWS; r++)
-#pragma unroll
-            for (int cc = 0; cc < 2; cc++) kr[0][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)(r * 2 + cc) * N));
         } else {
           // monomial factors (X^m - 1), (X^-m - 1) at this thread's 4 evaluation points, Montgomery form
           const u32 m = s_idx[gg * NPAD + step], mask = 2 * N - 1;
@@ -680,7 +705,7 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
 #pragma unroll
             for (int r = 0; r < ROWS; r++) {
               const u32 dval = sl == 0 ? dv[r].x : sl == 1 ? dv[r].y : sl == 2 ? dv[r].z : dv[r].w;
-              const uint4 kp = kr[0][r][cc];
+              const uint4 kp = kr[AP ? (j & 1) : 0][r][cc];
               sp += (u64)dval * (sl == 0 ? kp.x : sl == 1 ? kp.y : sl == 2 ? kp.z : kp.w);
               if (!AP) {
                 const uint4 kn = kr[AP ? 0 : 1][r][cc];
@@ -696,6 +721,9 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
           }
           // R[gg][cc] overwrites dct row cc: this thread has already consumed that chunk of every row
           *reinterpret_cast<uint4 *>(gd + (size_t)cc * N) = make_uint4(out[0], out[1], out[2], out[3]);
+        }
+        if (AP && j + 2 < JN) { // this buffer is free again: request the key of the gate after next
+          if ((j & 1) == 0) BFHE_AP_LOAD(0, ap_key(gs0 + (j + 2) * GS, qc)); else BFHE_AP_LOAD(1, ap_key(gs0 + (j + 2) * GS, qc));
         }
       }
     }
