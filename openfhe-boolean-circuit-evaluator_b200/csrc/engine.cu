@@ -77,6 +77,10 @@ extern "C" bfhe_ctx *bfhe_create(int paramset, int method, int device) {
     set_error("ring modulus outside (2^26, 2^27): the lazy-reduction ranges of the kernels assume 32Q < 2^32");
     return nullptr;
   }
+  if ((2 * p.N / p.q) % 2 != 0) {
+    set_error("2N/q must be even (the monomial-factor table of the external product holds even exponents only)");
+    return nullptr;
+  }
   if (kernels_built_for_solinas_q() && p.Q != (1ull << 27) - (1ull << 11) + 1) {
     set_error("kernels are specialised for Q = 2^27 - 2^11 + 1; rebuild with -DBFHE_GENERIC_Q for another modulus");
     return nullptr;

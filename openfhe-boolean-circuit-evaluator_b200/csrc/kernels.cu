@@ -123,6 +123,8 @@ __device__ __forceinline__ u32 csub(u32 x, u32 Q) { return min(x, x - Q); }     
 // pass) is E words; its 16-byte chunks are XOR-swizzled so that both the row access (LDS.128 by the
 // owning lane) and the column access (LDS.32 of index lane+32k by all lanes) are conflict free.
 // ------------------------------------------------------------------------------------------
+// position of entry u of the monomial-factor table: the low five bits are folded with the next five
+__device__ __forceinline__ u32 f_phys(u32 u) { return (u & ~31u) | ((u ^ (u >> 5)) & 31u); }
 template <int E> struct Lay {
   static constexpr int C = E / 4;
   __device__ __forceinline__ static int swz(int tp) { return E == 32 ? (tp & 7) : ((tp >> 1) & 3); }
@@ -416,8 +418,13 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
   const u32 Q = P.Q, q = P.q, n = P.n;
 
   for (int i = tid; i < 4 * N; i += Cfg::THREADS) s_tw[i] = g_twl[i];
-  if (!AP)
-    for (int i = tid; i < 2 * N; i += Cfg::THREADS) s_psiM[i] = g_psiM[i];
+  if (!AP) {
+    if constexpr (G > 4) { // register-lean form: psi^k table, factors by Montgomery product
+      for (int i = tid; i < 2 * N; i += Cfg::THREADS) s_psiM[i] = g_psiM[i];
+    } else { // monomial-factor table (psi^(2u) - 1), see the external product
+      for (int u = tid; u < N; u += Cfg::THREADS) s_psiM[f_phys((u32)u)] = (g_psiM[2 * u] + (P.Q - P.oneM)) % P.Q;
+    }
+  }
   const TwTabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
 
   // ---- prologue: LWE prep (EvalBinGate's ct1+ct2 / 2(ct1-ct2) / Bootstrap's b+q/4, with fused EvalNOT) ----
@@ -680,16 +687,15 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
         if (AP) {
         } else {
           // monomial factors (X^m - 1), (X^-m - 1) at this thread's 4 evaluation points, Montgomery form
-          const u32 m = s_idx[gg * NPAD + step], mask = 2 * N - 1;
-          const u32 ia = (m * eA) & mask;
-          const u32 A = s_psiM[ia], Ai = s_psiM[(2 * N - ia) & mask];
-          const u32 om = Q - P.oneM;
+          // (exponents are even -- m is a multiple of 2N/q = 2 -- so the table has N entries, (psi^(2u) - 1) * 2^32 mod Q at f_phys(u): one
+          // gather per factor instead of two gathers and a Montgomery product; the index fold keeps the 32 lanes of a warp, whose u differ
+          // in five consecutive bits t .. t+4 (t = number of trailing zeros of m), on 32 different banks for every t)
+          const u32 m = s_idx[gg * NPAD + step];
 #pragma unroll
           for (int r = 0; r < 4; r++) {
-            const u32 ib = (m * eB[r]) & mask;
-            const u32 Bv = s_psiM[ib], Bi = s_psiM[(2 * N - ib) & mask];
-            fp[r] = redc((u64)A * Bv, Q, P.qinv_neg) + om;
-            fn[r] = redc((u64)Ai * Bi, Q, P.qinv_neg) + om;
+            const u32 u = ((m * (eA + eB[r])) >> 1) & (N - 1);
+            fp[r] = s_psiM[f_phys(u)];
+            fn[r] = s_psiM[f_phys((0u - u) & (N - 1))];
           }
         }
         u32 *gd = dct + (size_t)gg * ROWS * N + Lay<E>::chunk_off(lane, qc);
