@@ -932,7 +932,7 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
 
   for (int i = tid; i < 4 * N; i += Cfg::THREADS) s_tw[i] = g_twl[i];
   if (!AP)
-    for (int i = tid; i < 2 * N; i += Cfg::THREADS) s_psiM[i] = g_psiM[i];
+    for (int u = tid; u < N; u += Cfg::THREADS) s_psiM[f_phys((u32)u)] = (g_psiM[2 * u] + (P.Q - P.oneM)) % P.Q; // (psi^(2u) - 1) * 2^32
   const TwTabs tt{s_tw, s_tw + N, s_tw + 2 * N, s_tw + 3 * N};
   if constexpr (QUAD) { // natural-order copy of the inverse twiddles: entry k < 32 from the kernel parameters, the rest out of the
                         // per-lane tables ([chunk][lane][4]: entry pp of lane L is twiddle groups * (32 + L) + gi)
@@ -1075,17 +1075,13 @@ blind_rotate_lat_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     for (int qc = warp; qc < C; qc += W) {
       u32 fp[4], fn[4];
       if (!AP) {
-        const u32 m = s_idx[step], mask = 2 * N - 1;
-        const u32 ia = (m * eA) & mask;
-        const u32 A = s_psiM[ia], Ai = s_psiM[(2 * N - ia) & mask];
-        const u32 om = Q - P.oneM;
+        const u32 m = s_idx[step]; // monomial-factor table, as in the throughput kernel
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           const u32 eB = 2 * ((brev(r, 2) << (LOGN - 2)) | (brev(qc, LOGN - 7) << 5));
-          const u32 ib = (m * eB) & mask;
-          const u32 Bv = s_psiM[ib], Bi = s_psiM[(2 * N - ib) & mask];
-          fp[r] = redc((u64)A * Bv, Q, P.qinv_neg) + om;
-          fn[r] = redc((u64)Ai * Bi, Q, P.qinv_neg) + om;
+          const u32 u = ((m * (eA + eB)) >> 1) & (N - 1);
+          fp[r] = s_psiM[f_phys(u)];
+          fn[r] = s_psiM[f_phys((0u - u) & (N - 1))];
         }
       }
       u32 *gd = dct + Lay<E>::chunk_off(lane, qc);
