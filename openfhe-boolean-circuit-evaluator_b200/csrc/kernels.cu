@@ -97,6 +97,9 @@ template <bool SOL = false> __device__ __forceinline__ u32 mul_shoup(u32 x, u32 
   }
 }
 // per-pass stage masks (bit i = stage i of the pass uses the ALU form); tuned with tools/perf_g.py / phase_timing.py
+#ifndef BFHE_KEY_HOIST
+#define BFHE_KEY_HOIST 1
+#endif
 #ifndef BFHE_SOL_THR_WIDE
 #define BFHE_SOL_THR_WIDE 0x00 // re-measured after the first-stage product table: 0x00/0x00 80.2k, 0x07/0x03 80.3k, 0x17/0x0b 79.7k,
 #define BFHE_SOL_THR_NARROW 0x00 // 0x1f/0x1f 77.1k gates/s -- within noise of each other except all-on; kept off
@@ -492,6 +495,13 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
 #define PT_T(i)
 #endif
   for (int step = 0; step < nsteps; step++) {
+    // key words of the external product (GINX: [sign][row][column]; AP: a double buffer over the gates, see below).  GINX, four gates per
+    // CTA: the first half is requested BEFORE the warp's last digit transform and the second half right after it, so the L2 round trip runs
+    // under the transform and the wait at the CTA barrier instead of in front of the product (BFHE_KEY_HOIST; 535 cycles of a 27 k-cycle step
+    // sat there, tools/phase_timing.py)
+    uint4 kr[2][ROWS][LEAN ? 1 : 2];
+    constexpr bool PAIRED_ANY = Cfg::LUT && !LEAN && (DG % 2 == 0) && G <= BFHE_PAIRED_MAXG && BFHE_PAIRED_DIGITS;
+    constexpr bool KEY_HOIST = !AP && !LEAN && !PAIRED_ANY && BFHE_KEY_HOIST;
     // ================= phase A: one warp per (gate, component) =================
     bool active = gvalid;
     if (AP && gvalid) active = s_idx[g * NPAD + step] != 0;
@@ -550,10 +560,23 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
           else x[k] = dgt + (Q - (1u << (LOGBG - 1)));
         }
         u32 *buf = dct + ((size_t)g * ROWS + c + 2 * l) * N;
+        if (KEY_HOIST && l == DG - 1 && warp < C * GS) {
+          const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + ((warp % C) * 32 + lane) * 4;
+#pragma unroll
+          for (int r = 0; r < ROWS; r++)
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) kr[0][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)(r * 2 + cc) * N));
+        }
         ntt_forward<LOGN, BFHE_SOL_THR_WIDE, BFHE_SOL_THR_NARROW, Cfg::LUT>(x, buf, P, tt, lane, pre);
         row_store<E>(buf, x, lane);
       }
       }
+    } else if (KEY_HOIST && warp < C * GS) { // empty gate slot (ragged last CTA): no transform to hide behind, but the product still needs the words
+      const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + ((warp % C) * 32 + lane) * 4;
+#pragma unroll
+      for (int r = 0; r < ROWS; r++)
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) kr[0][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)(r * 2 + cc) * N));
     }
     pending = pending || active;
     PT_T(0);
@@ -562,7 +585,6 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
     // AP: every gate has its own key (BK[i][digit][k]), so nothing is shared between the gates of the CTA; the two halves of kr[] are a
     // double buffer instead -- gate j's words are requested while gate j - 1 is multiplied (the first two before the barrier), which takes
     // the L2 round trip of 16 LDG.128 per gate and step off the critical path
-    uint4 kr[2][ROWS][LEAN ? 1 : 2];
     constexpr int JN = (G + GS - 1) / GS; // gates per item
     auto ap_key = [&](int gg, int qc) -> const u32 * { // this step's key of gate gg at chunk qc (no such gate, or digit 0 = step skipped: any
       const u32 a0 = gg < gcount ? s_idx[gg * NPAD + step] : 0u; // valid key, the words are loaded and not used -- unconditional loads keep kr[] in registers)
@@ -583,7 +605,7 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
     if (!AP && warp < C * GS) {
       const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + ((warp % C) * 32 + lane) * 4;
 #pragma unroll
-      for (int s = 0; s < 2; s++)
+      for (int s = KEY_HOIST ? 1 : 0; s < 2; s++)
 #pragma unroll
         for (int r = 0; r < ROWS; r++)
 #pragma unroll
