@@ -97,8 +97,11 @@ template <bool SOL = false> __device__ __forceinline__ u32 mul_shoup(u32 x, u32 
   }
 }
 // per-pass stage masks (bit i = stage i of the pass uses the ALU form); tuned with tools/perf_g.py / phase_timing.py
+#ifndef BFHE_AP_HOIST
+#define BFHE_AP_HOIST 0
+#endif
 #ifndef BFHE_KEY_HOIST
-#define BFHE_KEY_HOIST 1
+#define BFHE_KEY_HOIST 2 // halves of the key tile requested before the last digit transform (measured: 0: 84.95 k, 1: 86.7 k, 2: 88.2 k gates/s)
 #endif
 #ifndef BFHE_SOL_THR_WIDE
 #define BFHE_SOL_THR_WIDE 0x00 // re-measured after the first-stage product table: 0x00/0x00 80.2k, 0x07/0x03 80.3k, 0x17/0x0b 79.7k,
@@ -502,6 +505,26 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
     uint4 kr[2][ROWS][LEAN ? 1 : 2];
     constexpr bool PAIRED_ANY = Cfg::LUT && !LEAN && (DG % 2 == 0) && G <= BFHE_PAIRED_MAXG && BFHE_PAIRED_DIGITS;
     constexpr bool KEY_HOIST = !AP && !LEAN && !PAIRED_ANY && BFHE_KEY_HOIST;
+    // AP: hoisting the first gate's key the same way helps one wave (47.3 k -> 48.8 k gates/s at 592 gates) and hurts eight (47.4 k -> 45.5 k at
+    // 4 736: the 2 GB key does not stay in L2 and the earlier requests spread the CTAs' working set); off
+    constexpr bool AP_HOIST = AP && !LEAN && !PAIRED_ANY && BFHE_KEY_HOIST && BFHE_AP_HOIST;
+    // AP: every gate has its own key (BK[i][digit][k]), so nothing is shared between the gates of the CTA; the two halves of kr[] are a
+    // double buffer instead -- gate j's words are requested while gate j - 1 is multiplied (the first two before the barrier), which takes
+    // the L2 round trip of 16 LDG.128 per gate and step off the critical path
+    constexpr int JN = (G + GS - 1) / GS; // gates per item
+    auto ap_key = [&](int gg, int qc) -> const u32 * { // this step's key of gate gg at chunk qc (no such gate, or digit 0 = step skipped: any
+      const u32 a0 = gg < gcount ? s_idx[gg * NPAD + step] : 0u; // valid key, the words are loaded and not used -- unconditional loads keep kr[] in registers)
+      const u32 i = step / P.dR, k = step % P.dR;
+      return bk + (((size_t)i * (P.baseR - 1) + (a0 ? a0 - 1 : 0u)) * P.dR + k) * (ROWS * 2) * N + (qc * 32 + lane) * 4;
+    };
+#define BFHE_AP_LOAD(buf, kb)                                                                                          \
+  do {                                                                                                                 \
+    const u32 *kb_ = (kb);                                                                                             \
+    _Pragma("unroll") for (int r = 0; r < ROWS; r++)                                                                   \
+      _Pragma("unroll") for (int cc = 0; cc < (LEAN ? 1 : 2); cc++)                                                    \
+        kr[buf][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb_ + (size_t)(r * 2 + cc) * N));                        \
+  } while (0)
+
     // ================= phase A: one warp per (gate, component) =================
     bool active = gvalid;
     if (AP && gvalid) active = s_idx[g * NPAD + step] != 0;
@@ -560,52 +583,43 @@ blind_rotate_kernel(const __grid_constant__ DevConst P, const DevGate *__restric
           else x[k] = dgt + (Q - (1u << (LOGBG - 1)));
         }
         u32 *buf = dct + ((size_t)g * ROWS + c + 2 * l) * N;
+        if (AP_HOIST && l == DG - 1 && warp < C * GS) BFHE_AP_LOAD(0, ap_key(warp / C, warp % C));
         if (KEY_HOIST && l == DG - 1 && warp < C * GS) {
           const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + ((warp % C) * 32 + lane) * 4;
 #pragma unroll
+          for (int sg = 0; sg < BFHE_KEY_HOIST; sg++)
+#pragma unroll
           for (int r = 0; r < ROWS; r++)
 #pragma unroll
-            for (int cc = 0; cc < 2; cc++) kr[0][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)(r * 2 + cc) * N));
+            for (int cc = 0; cc < 2; cc++) kr[sg][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((sg * ROWS + r) * 2 + cc) * N));
         }
         ntt_forward<LOGN, BFHE_SOL_THR_WIDE, BFHE_SOL_THR_NARROW, Cfg::LUT>(x, buf, P, tt, lane, pre);
         row_store<E>(buf, x, lane);
       }
       }
+    } else if (AP_HOIST && warp < C * GS) { // this warp's gate skips the step (digit 0) or does not exist: no transform to hide behind
+      BFHE_AP_LOAD(0, ap_key(warp / C, warp % C));
     } else if (KEY_HOIST && warp < C * GS) { // empty gate slot (ragged last CTA): no transform to hide behind, but the product still needs the words
       const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + ((warp % C) * 32 + lane) * 4;
 #pragma unroll
+      for (int sg = 0; sg < BFHE_KEY_HOIST; sg++)
+#pragma unroll
       for (int r = 0; r < ROWS; r++)
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) kr[0][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)(r * 2 + cc) * N));
+        for (int cc = 0; cc < 2; cc++) kr[sg][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb + (size_t)((sg * ROWS + r) * 2 + cc) * N));
     }
     pending = pending || active;
     PT_T(0);
     // GINX: this warp's first key chunk is requested BEFORE the barrier, so the L2 round trip overlaps the wait for
     // the slower warps of the CTA instead of stalling the external product (ncu r1: 6 % of samples sat on these loads)
-    // AP: every gate has its own key (BK[i][digit][k]), so nothing is shared between the gates of the CTA; the two halves of kr[] are a
-    // double buffer instead -- gate j's words are requested while gate j - 1 is multiplied (the first two before the barrier), which takes
-    // the L2 round trip of 16 LDG.128 per gate and step off the critical path
-    constexpr int JN = (G + GS - 1) / GS; // gates per item
-    auto ap_key = [&](int gg, int qc) -> const u32 * { // this step's key of gate gg at chunk qc (no such gate, or digit 0 = step skipped: any
-      const u32 a0 = gg < gcount ? s_idx[gg * NPAD + step] : 0u; // valid key, the words are loaded and not used -- unconditional loads keep kr[] in registers)
-      const u32 i = step / P.dR, k = step % P.dR;
-      return bk + (((size_t)i * (P.baseR - 1) + (a0 ? a0 - 1 : 0u)) * P.dR + k) * (ROWS * 2) * N + (qc * 32 + lane) * 4;
-    };
-#define BFHE_AP_LOAD(buf, kb)                                                                                          \
-  do {                                                                                                                 \
-    const u32 *kb_ = (kb);                                                                                             \
-    _Pragma("unroll") for (int r = 0; r < ROWS; r++)                                                                   \
-      _Pragma("unroll") for (int cc = 0; cc < (LEAN ? 1 : 2); cc++)                                                    \
-        kr[buf][r][cc] = __ldg(reinterpret_cast<const uint4 *>(kb_ + (size_t)(r * 2 + cc) * N));                        \
-  } while (0)
     if (AP && !LEAN && warp < C * GS) {
-      BFHE_AP_LOAD(0, ap_key(warp / C, warp % C));
+      if (!AP_HOIST) BFHE_AP_LOAD(0, ap_key(warp / C, warp % C));
       if (JN > 1) BFHE_AP_LOAD(1, ap_key(warp / C + GS, warp % C));
     }
     if (!AP && warp < C * GS) {
       const u32 *kb = bk + (size_t)step * (2 * ROWS * 2) * N + ((warp % C) * 32 + lane) * 4;
 #pragma unroll
-      for (int s = KEY_HOIST ? 1 : 0; s < 2; s++)
+      for (int s = KEY_HOIST ? BFHE_KEY_HOIST : 0; s < 2; s++)
 #pragma unroll
         for (int r = 0; r < ROWS; r++)
 #pragma unroll
