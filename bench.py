@@ -42,7 +42,7 @@ BK_BYTES = 65_798_144
 KS_ROW_BYTES = 1024 * 2 * 1024  # 2048 padded 1 KiB rows
 IO_BYTES = 3 * 504 * 4
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of the throughput kernel (see roofline.traffic_source)
-STATIC_TRAFFIC = {"bytes": 73.35e6, "gates": 592, "source": "profiles/r1_blind_rotate_ncu_summary.md"}
+STATIC_TRAFFIC = {"bytes": 74.46e6, "gates": 592, "source": "profiles/r2_blind_rotate_ncu_summary.md"}
 
 
 def parse():
