@@ -1290,13 +1290,13 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // Which variant?  Measured on B200, STD128_OPT GINX (profiles/): one gate on four SMs 1.02 ms per wave of up to 33 gates; one gate on two
-  // SMs 1.49 ms up to 74; latency form (one gate per CTA) 2.3 ms per wave of `sms` gates; throughput form (4 gates per CTA share every
-  // key word) 7.4 ms per wave of 4 * sms gates.  Narrow circuit levels go to the cluster forms, wide batches to the throughput form.
+  // Which variant?  Measured on B200, STD128_OPT GINX (profiles/): one gate on four SMs 0.98 ms per wave of up to 33 gates; one gate on two
+  // SMs 1.48 ms up to 74; latency form (one gate per CTA) 2.22 ms per wave of `sms` gates; throughput form (4 gates per CTA share every
+  // key word) 6.7 ms per wave of 4 * sms gates.  Narrow circuit levels go to the cluster forms, wide batches to the throughput form.
   if (force_g == 0 && have_clx && count <= clx_fast_gates()) return launch_blind_rotate_clx(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   if (force_g == 0 && have_cl2 && count <= cl2_max_gates()) return launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
-  const long lat_cost = (long)((count + sms - 1) / sms) * 23;
-  const long thr_cost = (long)((count + 4 * sms - 1) / (4 * sms)) * 76;
+  const long lat_cost = (long)((count + sms - 1) / sms) * 222;           // 2.22 ms per wave of `sms` gates
+  const long thr_cost = (long)((count + 4 * sms - 1) / (4 * sms)) * 670; // 6.70 ms per wave of 4 * sms gates
   const bool lat = force_g == 8 || (force_g == 0 && lat_cost <= thr_cost);
   if (lat) {
     if (P.N == 1024 && P.dG == 4 && P.logBG == 7)
