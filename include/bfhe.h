@@ -133,8 +133,8 @@ int bfhe_dbg_ntt_roundtrip(bfhe_ctx *, const uint32_t *poly_host, size_t npoly, 
 /* blind rotation only: acc in coefficient form (2N words per gate) */
 int bfhe_dbg_blind_rotate(bfhe_ctx *, uint32_t *dev_slab, const bfhe_gate *gates, size_t count, uint32_t *acc_host);
 /* test hook: force the blind-rotation form.  0 = cost model; 1, 2, 4 = that many gates per CTA (first-generation throughput
- * kernel); 8 = one gate per CTA, TMA-staged key (latency kernel); 16 = 16-warp throughput kernel; 32 / 64 = one gate on a 2- / 4-CTA
- * thread-block cluster (16, 32, 64: STD128_OPT GINX only) */
+ * kernel); 8 = one gate per CTA, TMA-staged key (latency kernel); 32 = one gate on a 2-CTA thread-block cluster (STD128_OPT GINX);
+ * 128 = one gate on a slot-sliced 4-CTA cluster (STD128_OPT, GINX and AP).  16 and 64 named round-1 forms that no longer exist. */
 int bfhe_dbg_set_gates_per_cta(bfhe_ctx *, int gates_per_cta);
 /* how many gates the 2-CTA / 4-CTA cluster forms keep co-resident on this device (cudaOccupancyMaxActiveClusters; differs between GPUs) */
 int bfhe_dbg_cluster_limits(bfhe_ctx *, int *cl2_gates, int *cl4_gates);

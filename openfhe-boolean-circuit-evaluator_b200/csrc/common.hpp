@@ -82,9 +82,9 @@ size_t clx_tw_words();
 int clx_set_attrs();
 int clx_max_gates();  // 4-CTA clusters the device keeps co-resident
 int clx_fast_gates(); // up to this many gates the 4-CTA form runs all clusters in one round at full speed
-int launch_bk_slice_clx(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream);
-int launch_blind_rotate_clx(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
-                            void *stream, LaunchInfo *info);
+int launch_bk_slice_clx(const u32 *d_src, u32 *d_dst, size_t npoly, int method_ap, void *stream);
+int launch_blind_rotate_clx(const DevConst &P, int method_ap, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext,
+                            u32 *d_acc_dbg, void *stream, LaunchInfo *info);
 // Multi-GPU exchange fused into the key switch: every output ciphertext is stored into every rank's wire slab (the peers'
 // slabs are mapped through CUDA IPC, the stores travel over NVLink), and the last CTA of the launch raises this rank's flag in every
 // peer's flag array.  Flag values only grow: value(epoch, index) = epoch * per_epoch + index + 1, `epoch` read from device memory so

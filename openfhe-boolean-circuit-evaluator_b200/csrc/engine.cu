@@ -418,7 +418,7 @@ int bfhe::ensure_device_keys(bfhe_ctx *c) {
   cudaFree(c->d_bkx); c->d_bkx = nullptr; c->v2.d_bkx = nullptr;
   if (c->d_twx && clx_supported(c->P, p.method == BFHE_AP)) { // key copy of the slot-sliced cluster kernel: [step][rank][polynomial][N/4]
     BFHE_CUDA(cudaMalloc(&c->d_bkx, c->bk_words * 4));
-    int rc = launch_bk_slice_clx(c->d_bk, c->d_bkx, c->bk_words / N, c->stream);
+    int rc = launch_bk_slice_clx(c->d_bk, c->d_bkx, c->bk_words / N, p.method == BFHE_AP, c->stream);
     if (rc) return cuda_fail((cudaError_t)rc, "bk_slice_clx");
     BFHE_CUDA(cudaStreamSynchronize(c->stream));
     c->v2.d_bkx = c->d_bkx;

@@ -1283,8 +1283,8 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   if (count <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const bool have_cl2 = v2 && v2->d_bk4 && v2->d_tw2 && v2->d_F && v2_supported(P, method_ap);
-  const bool have_clx = v2 && v2->d_bkx && v2->d_twx && v2->d_F && clx_supported(P, method_ap);
-  if (force_g == 128) return have_clx ? launch_blind_rotate_clx(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info) : (int)cudaErrorInvalidValue;
+  const bool have_clx = v2 && v2->d_bkx && v2->d_twx && (method_ap || v2->d_F) && clx_supported(P, method_ap);
+  if (force_g == 128) return have_clx ? launch_blind_rotate_clx(P, method_ap, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info) : (int)cudaErrorInvalidValue;
   if (force_g == 32) return have_cl2 ? launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info) : (int)cudaErrorInvalidValue;
   if (force_g != 0 && force_g != 1 && force_g != 2 && force_g != 4 && force_g != 8) return (int)cudaErrorInvalidValue;
   int dev = 0, sms = 148;
@@ -1293,7 +1293,7 @@ int launch_blind_rotate(const DevConst &P, int method_ap, const DevGate *d_gates
   // Which variant?  Measured on B200, STD128_OPT GINX (profiles/): one gate on four SMs 0.98 ms per wave of up to 33 gates; one gate on two
   // SMs 1.48 ms up to 74; latency form (one gate per CTA) 2.22 ms per wave of `sms` gates; throughput form (4 gates per CTA share every
   // key word) 6.7 ms per wave of 4 * sms gates.  Narrow circuit levels go to the cluster forms, wide batches to the throughput form.
-  if (force_g == 0 && have_clx && count <= clx_fast_gates()) return launch_blind_rotate_clx(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
+  if (force_g == 0 && have_clx && count <= clx_fast_gates()) return launch_blind_rotate_clx(P, method_ap, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   if (force_g == 0 && have_cl2 && count <= cl2_max_gates()) return launch_blind_rotate_cl2(P, d_gates, count, *v2, d_ext, d_acc_dbg, stream, info);
   const long lat_cost = (long)((count + sms - 1) / sms) * 222;           // 2.22 ms per wave of `sms` gates
   const long thr_cost = (long)((count + 4 * sms - 1) / (4 * sms)) * 670; // 6.70 ms per wave of 4 * sms gates

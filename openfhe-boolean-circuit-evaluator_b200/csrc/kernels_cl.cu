@@ -45,7 +45,8 @@ namespace bfhe {
 namespace clx {
 
 constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, NPAD = 512, R = 4, NB = N / R, THREADS = 288; // 8 main warps + the warp that fetches the key tiles
-constexpr int KEYPOLYS = 2 * ROWS * 2;
+constexpr int KEYPOLYS = 2 * ROWS * 2; // GINX: two RGSW ciphertexts (X^a, X^-a) per step; AP: one (KEYPOLYS / 2 polynomials)
+constexpr int NSTEP_PAD = 1024;     // >= n (GINX) and >= n * dR (AP)
 constexpr u32 DIGIT_OFF = 64u + (64u << 7) + (64u << 14) + (64u << 21);
 constexpr u32 SOLINAS_Q = (1u << 27) - (1u << 11) + 1;
 
@@ -174,13 +175,14 @@ struct Smem { // word offsets
   static constexpr int lut = accs + 2 * N;                    // [3][128][32]
   static constexpr int F = lut + 3 * 128 * 32;                // [2N]
   static constexpr int key = F + 2 * N;                       // [parity 2][8 quads][NB][4]
-  static constexpr int idx = key + 2 * KEYPOLYS * NB;         // u16 [NPAD]
-  static constexpr int bars = idx + NPAD / 2;                 // rbar[parity 2][component 2], kbar[2]
+  static constexpr int idx = key + 2 * KEYPOLYS * NB;         // u16 [NSTEP_PAD] monomial exponent (GINX) / digit (AP) per step
+  static constexpr int list = idx + NSTEP_PAD / 2;            // u16 [NSTEP_PAD] AP: the steps that do work (digit != 0)
+  static constexpr int bars = list + NSTEP_PAD / 2;           // rbar[parity 2][component 2], kbar[2]
   static constexpr int words = bars + 12;
   static constexpr size_t bytes = (size_t)words * 4;
 };
 static_assert(Smem::key % 32 == 0 && Smem::bars % 2 == 0, "TMA destination 128-byte aligned, mbarriers 8-byte aligned");
-constexpr u32 KEYBYTES = KEYPOLYS * NB * 4;     // this CTA's quarter of one step's key tile
+constexpr u32 KEYBYTES = KEYPOLYS * NB * 4;     // this CTA's quarter of one step's key tile (GINX; AP: half of it)
 constexpr u32 RECV_TX_C = (u32)(R - 1) * NB * 4; // bytes the three peers push into a CTA per step and component
 
 // named barriers (0 is left to __syncthreads in the prologue)
@@ -188,6 +190,7 @@ constexpr int BAR_DCT = 1, BAR_GROUP = 2 /* + c */, BAR_KEY = 4;
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+template <bool AP>
 __global__ void __cluster_dims__(R, 1, 1) __launch_bounds__(THREADS, 1)
 blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__restrict__ gates, int count, const u32 *__restrict__ bkx,
                         const u32 *__restrict__ g_tw, const u32 *__restrict__ g_F, u32 *__restrict__ ext, u32 *__restrict__ acc_dbg) {
@@ -195,10 +198,10 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   u32 *sm = reinterpret_cast<u32 *>(smem_raw);
   u32 *rbuf = sm + Smem::rbuf, *dct = sm + Smem::dct, *pbuf = sm + Smem::pbuf, *accs = sm + Smem::accs, *s_lut = sm + Smem::lut, *s_F = sm + Smem::F,
       *s_key = sm + Smem::key;
-  u16 *s_idx = reinterpret_cast<u16 *>(sm + Smem::idx);
+  u16 *s_idx = reinterpret_cast<u16 *>(sm + Smem::idx), *s_list = reinterpret_cast<u16 *>(sm + Smem::list);
   u64 *rbar = reinterpret_cast<u64 *>(sm + Smem::bars); // [parity][component]
   u64 *kbar = rbar + 4;
-  __shared__ u32 s_b;
+  __shared__ u32 s_b, s_nact;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 k = cluster_rank();
@@ -211,7 +214,8 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     mbar_init(kbar + 0, 1); mbar_init(kbar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 2 * N; i += THREADS) s_F[i] = g_F[i];
+  if (!AP)
+    for (int i = tid; i < 2 * N; i += THREADS) s_F[i] = g_F[i];
   { // look-up tables of the two cross-block forward stages for block k: y_k = d0 + c1 d2 + c2 d1 + c3 d3 with
     //   k = 0: (+w1, +w2, +w2 w1)   k = 1: (+w1, -w2, -w2 w1)   k = 2: (-w1, +w3, -w3 w1)   k = 3: (-w1, -w3, +w3 w1)
     // (w1 = psi^bitrev(1), w2 = psi^bitrev(2), w3 = psi^bitrev(3): the twiddles of the stages with 1 and 2 groups), entries
@@ -242,18 +246,37 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
         v = (gate == OP_XOR_FAST || gate == OP_XNOR_FAST) ? (2 * (x + q - y)) % q : (x + y) % q;
       }
       if (i == n) s_b = v;
-      else s_idx[i] = (u16)(((q - v) % q) * P.factor);
+      else if (!AP) s_idx[i] = (u16)(((q - v) % q) * P.factor);
+      else { // AP: digits of -a_i in base B_r, one step each; BK[i][digit][k] (digit 0: nothing to do)
+        u32 a = (q - v) % q;
+        for (u32 kk = 0; kk < P.dR; kk++, a /= P.baseR) s_idx[i * P.dR + kk] = (u16)(a % P.baseR);
+      }
     }
   }
   __syncthreads();
+  if (AP && tid == 0) { // the steps that do work, in order
+    u32 na = 0;
+    for (u32 st = 0; st < n * P.dR; st++)
+      if (s_idx[st] != 0) s_list[na++] = (u16)st;
+    s_nact = na;
+  }
+  if (AP) __syncthreads();
+  const u32 nact = AP ? s_nact : n; // iterations of the main loop
 
-  auto issue_keys = [&](u32 step) { // one thread: this CTA's 32 KB of step `step`, [step][rank][quad][slot][4] contiguous
-    u64 *bar = kbar + (step & 1);
-    mbar_expect_tx(bar, KEYBYTES);
-    const u32 *src = bkx + ((size_t)step * R + k) * KEYPOLYS * NB;
-    u32 *dst = s_key + (size_t)(step & 1) * KEYPOLYS * NB;
-    bulk_g2s(dst, src, 16384, bar);
-    bulk_g2s(dst + 4096, src + 4096, 16384, bar);
+  auto issue_keys = [&](u32 j) { // one thread: this CTA's key tile of iteration j (GINX 32 KB, AP 16 KB), contiguous in the sliced copy
+    u64 *bar = kbar + (j & 1);
+    u32 *dst = s_key + (size_t)(j & 1) * KEYPOLYS * NB;
+    if (!AP) {
+      mbar_expect_tx(bar, KEYBYTES);
+      const u32 *src = bkx + ((size_t)j * R + k) * KEYPOLYS * NB;
+      bulk_g2s(dst, src, 16384, bar);
+      bulk_g2s(dst + 4096, src + 4096, 16384, bar);
+    } else {
+      const u32 st = s_list[j], a0 = s_idx[st], i = st / P.dR, kk = st % P.dR;
+      const size_t keyi = ((size_t)i * (P.baseR - 1) + (a0 - 1)) * P.dR + kk;
+      mbar_expect_tx(bar, KEYBYTES / 2);
+      bulk_g2s(dst, bkx + (keyi * R + k) * (KEYPOLYS / 2) * NB, 16384, bar);
+    }
   };
   static_assert(KEYBYTES == 2 * 16384, "two bulk copies");
 
@@ -268,12 +291,12 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
 
   if (warp >= 8) {
     // ================= ninth warp: fetches the key tiles (TMA bulk copies, two steps ahead) =================
-    if (lane == 0 && n > 0) {
+    if (lane == 0 && nact > 0) {
       issue_keys(0);
-      if (n > 1) issue_keys(1);
+      if (nact > 1) issue_keys(1);
     }
     cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
-    for (u32 step = 0; step + 2 < n; step++) {
+    for (u32 step = 0; step + 2 < nact; step++) {
       bar_sync(BAR_KEY, 256 + 32); // all product threads are through with this step's key tile
       if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // their reads of the buffer, before the async proxy overwrites it
@@ -334,7 +357,7 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
   }
   cluster_sync_all(); // every CTA's mbarriers are initialised before anything is pushed
 
-  for (u32 step = 0; step < n; step++) {
+  for (u32 step = 0; step < nact; step++) { // (AP: `step` counts the steps that do work; s_list[step] is the blind-rotation step)
     const u32 par = step & 1;
 #ifdef BFHE_PHASE_TIMING
     tstep = step;
@@ -342,8 +365,10 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
     // the key tile of this step was requested two steps ago: test its barrier once now (the ~100 cycles of a try_wait then overlap the
     // transform); the monomial factors do not depend on the transform either
     const bool key_in = mbar_test(kbar + par, (step >> 1) & 1);
-    const u32 mono0 = s_idx[step] * ex0, mono1 = s_idx[step] * ex1; // (X^m - 1), (X^-m - 1) at my two slots, Montgomery form
-    const u32 fp[2] = {s_F[f_index(mono0)], s_F[f_index(mono1)]}, fn[2] = {s_F[f_index(0u - mono0)], s_F[f_index(0u - mono1)]};
+    const u32 mexp = AP ? 0u : (u32)s_idx[step];
+    const u32 mono0 = mexp * ex0, mono1 = mexp * ex1; // GINX: (X^m - 1), (X^-m - 1) at my two slots, Montgomery form
+    const u32 fp[2] = {AP ? 0u : s_F[f_index(mono0)], AP ? 0u : s_F[f_index(mono1)]},
+              fn[2] = {AP ? 0u : s_F[f_index(0u - mono0)], AP ? 0u : s_F[f_index(0u - mono1)]};
     // ---- phase A: my group's accumulator words are published -> block k of the two cross-block forward stages of MY row, by look-up ----
     bar_sync(BAR_GROUP + c, 128);
     CLX_T(0);
@@ -391,10 +416,11 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
 #pragma unroll
       for (int rw = 0; rw < ROWS; rw++) d[rw] = *reinterpret_cast<const uint2 *>(dct + (par * ROWS + rw) * NB + 2 * gt);
       // key tile: [quad g = (cc * 2 + sign) * 2 + half][slot parity e][gt][4 rows]
-      const uint4 *k4 = reinterpret_cast<const uint4 *>(s_key + (size_t)par * KEYPOLYS * NB) + (size_t)c * 4 * 2 * 128 + gt;
+      // (AP: one RGSW ciphertext per step -- quad g = cc * 2 + half, no sign)
+      const uint4 *k4 = reinterpret_cast<const uint4 *>(s_key + (size_t)par * KEYPOLYS * NB) + (size_t)c * (AP ? 2 : 4) * 2 * 128 + gt;
       u64 s2[2][2] = {{0, 0}, {0, 0}}; // [slot parity][sign]
 #pragma unroll
-      for (int sg = 0; sg < 2; sg++)
+      for (int sg = 0; sg < (AP ? 1 : 2); sg++)
 #pragma unroll
         for (int hf = 0; hf < 2; hf++) {
           const uint4 k0 = k4[((sg * 2 + hf) * 2 + 0) * 128], k1 = k4[((sg * 2 + hf) * 2 + 1) * 128];
@@ -403,8 +429,14 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
           s2[0][sg] += (u64)d[4 * hf + 2].x * k0.z; s2[1][sg] += (u64)d[4 * hf + 2].y * k1.z;
           s2[0][sg] += (u64)d[4 * hf + 3].x * k0.w; s2[1][sg] += (u64)d[4 * hf + 3].y * k1.w;
         }
-      u32 v0 = redc((u64)redc(s2[0][0], Q, qinv) * fp[0] + (u64)redc(s2[0][1], Q, qinv) * fn[0], Q, qinv); // < 2Q
-      u32 v1 = redc((u64)redc(s2[1][0], Q, qinv) * fp[1] + (u64)redc(s2[1][1], Q, qinv) * fn[1], Q, qinv);
+      u32 v0, v1; // < 2Q
+      if (AP) { // one Montgomery reduction of a sum of 8 products of (< 21 Q) x (< Q): < 7 Q, pulled back below 2 Q
+        v0 = lazy_reduce(redc(s2[0][0], Q, qinv), Q); v1 = lazy_reduce(redc(s2[1][0], Q, qinv), Q);
+      }
+      else {
+        v0 = redc((u64)redc(s2[0][0], Q, qinv) * fp[0] + (u64)redc(s2[0][1], Q, qinv) * fn[0], Q, qinv);
+        v1 = redc((u64)redc(s2[1][0], Q, qinv) * fp[1] + (u64)redc(s2[1][1], Q, qinv) * fn[1], Q, qinv);
+      }
       CLX_T(5);
       { // half-size 1: my two slots are the pair (bound 2 -> 4)
         const u32 df = v0 - v1 + 2 * Q;
@@ -425,7 +457,7 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
       // peers (stores that landed earlier merely ran the count negative)
       if (gt == 0) mbar_expect_tx(rbar + par * 2 + c, RECV_TX_C);
       else mbar_arrive(rbar + par * 2 + c);
-      if (step + 2 < n) bar_arrive(BAR_KEY, 256 + 32); // the ninth warp may overwrite this step's key tile
+      if (step + 2 < nact) bar_arrive(BAR_KEY, 256 + 32); // the ninth warp may overwrite this step's key tile
     }
     CLX_T(6);
     // ---- phase E: my component's four partial rows have landed (mine stored above, the peers' by bulk copy).  Warp l of the group runs the
@@ -457,10 +489,11 @@ blind_rotate_clx_kernel(const __grid_constant__ DevConst P, const DevGate *__res
       const u32 u2 = p2 + p3, u3 = mul_shoup(p2 - p3 + 4 * Q, iwc, iwcs, Q);
       const u32 x0 = u0 + u2, x2 = mul_shoup(u0 - u2 + 8 * Q, iw1, iw1s, Q); // u0, u2 < 8Q
       const u32 x1 = u1 + u3, x3 = mul_shoup(u1 - u3 + 2 * Q, iw1, iw1s, Q); // u1, u3 < 2Q
-      acc[jj][0] = csub(acc[jj][0] + csub(lazy_reduce(x0, Q), Q), Q);
-      acc[jj][1] = csub(acc[jj][1] + csub(lazy_reduce(x1, Q), Q), Q);
-      acc[jj][2] = csub(acc[jj][2] + csub(x2, Q), Q);
-      acc[jj][3] = csub(acc[jj][3] + csub(x3, Q), Q);
+      // GINX: acc += (X^a - 1) acc (x) key+ + (X^-a - 1) acc (x) key-;  AP: acc = acc (x) key[digit]
+      acc[jj][0] = csub((AP ? 0u : acc[jj][0]) + csub(lazy_reduce(x0, Q), Q), Q);
+      acc[jj][1] = csub((AP ? 0u : acc[jj][1]) + csub(lazy_reduce(x1, Q), Q), Q);
+      acc[jj][2] = csub((AP ? 0u : acc[jj][2]) + csub(x2, Q), Q);
+      acc[jj][3] = csub((AP ? 0u : acc[jj][3]) + csub(x3, Q), Q);
 #pragma unroll
       for (int i1 = 0; i1 < 4; i1++) {
         const u32 a = acc[jj][i1];
@@ -518,10 +551,24 @@ __global__ void bk_slice_clx_kernel(const u32 *__restrict__ src, u32 *__restrict
   }
 }
 
+// AP: one RGSW ciphertext (KEYPOLYS / 2 polynomials, [row][column]) per key; [key][rank][quad g = cc * 2 + half][slot parity e][gt][4]
+__global__ void bk_slice_clx_ap_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst, size_t nkeys) {
+  constexpr int KP = KEYPOLYS / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nkeys * KP * N; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t key = i / ((size_t)KP * N), rem = i % ((size_t)KP * N);
+    const int rk = (int)(rem / ((size_t)KP * NB)), g = (int)((rem / (NB * 4)) % 4), e = (int)((rem / (128 * 4)) % 2), gt = (int)((rem / 4) % 128),
+              w4 = (int)(rem % 4);
+    const int cc = g >> 1, hf = g & 1, rw = 4 * hf + w4, t = 2 * gt + e;
+    const int pl = rw * 2 + cc;
+    const int Ppos = slot_position(rk, t), sl = Ppos >> 5, j = Ppos & 31;
+    dst[i] = src[(key * KP + pl) * N + ((j >> 2) * 32 + sl) * 4 + (j & 3)];
+  }
+}
+
 } // namespace clx
 
 bool clx_supported(const DevConst &P, int method_ap) {
-  return !method_ap && P.N == 1024 && P.dG == 4 && P.logBG == 7 && P.Q == clx::SOLINAS_Q && P.n <= (u32)clx::NPAD;
+  return P.N == 1024 && P.dG == 4 && P.logBG == 7 && P.Q == clx::SOLINAS_Q && P.n * (method_ap ? P.dR : 1u) <= (u32)clx::NSTEP_PAD;
 }
 size_t clx_tw_words() { return (size_t)clx::R * clx::TWR; }
 static int clx_device_slot() {
@@ -530,7 +577,9 @@ static int clx_device_slot() {
   return dev >= 0 && dev < 64 ? dev : 0;
 }
 int clx_set_attrs() {
-  return (int)cudaFuncSetAttribute(clx::blind_rotate_clx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clx::Smem::bytes);
+  int rc = (int)cudaFuncSetAttribute(clx::blind_rotate_clx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clx::Smem::bytes);
+  rc |= (int)cudaFuncSetAttribute(clx::blind_rotate_clx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clx::Smem::bytes);
+  return rc;
 }
 static int clx_attrs_once() { // per device, and never under stream capture: at first use
   static bool done[64];
@@ -556,7 +605,7 @@ int clx_max_gates() { // 4-CTA clusters of this kernel the device keeps co-resid
       at[0].val.clusterDim.x = clx::R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      if (cudaOccupancyMaxActiveClusters(&nmax, clx::blind_rotate_clx_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nmax = 0; }
+      if (cudaOccupancyMaxActiveClusters(&nmax, clx::blind_rotate_clx_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); nmax = 0; }
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -570,18 +619,23 @@ int clx_max_gates() { // 4-CTA clusters of this kernel the device keeps co-resid
 // The occupancy query is exact for this kernel (B200: 33 clusters; measured 1.02 ms per wave up to 33 gates, 2.03 ms -- a second round --
 // from 34 on), so the whole co-resident maximum runs at full speed.
 int clx_fast_gates() { return clx_max_gates(); }
-int launch_bk_slice_clx(const u32 *d_src, u32 *d_dst, size_t npoly, void *stream) {
+int launch_bk_slice_clx(const u32 *d_src, u32 *d_dst, size_t npoly, int method_ap, void *stream) {
   if (npoly == 0) return 0;
-  clx::bk_slice_clx_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly / clx::KEYPOLYS);
+  if (method_ap) clx::bk_slice_clx_ap_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly / (clx::KEYPOLYS / 2));
+  else clx::bk_slice_clx_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, npoly / clx::KEYPOLYS);
   return (int)cudaGetLastError();
 }
-int launch_blind_rotate_clx(const DevConst &P, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg, void *stream,
-                            LaunchInfo *info) {
+int launch_blind_rotate_clx(const DevConst &P, int method_ap, const DevGate *d_gates, int count, const V2Bufs &vb, u32 *d_ext, u32 *d_acc_dbg,
+                            void *stream, LaunchInfo *info) {
   if (count <= 0) return 0;
   if (int rc = clx_attrs_once()) return rc;
   if (info) { info->gates_per_cta = 1; info->ctas = clx::R * count; info->smem_bytes = clx::Smem::bytes; }
-  clx::blind_rotate_clx_kernel<<<clx::R * count, clx::THREADS, clx::Smem::bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bkx, vb.d_twx, vb.d_F,
-                                                                                                   d_ext, d_acc_dbg);
+  if (method_ap)
+    clx::blind_rotate_clx_kernel<true><<<clx::R * count, clx::THREADS, clx::Smem::bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bkx, vb.d_twx,
+                                                                                                           vb.d_F, d_ext, d_acc_dbg);
+  else
+    clx::blind_rotate_clx_kernel<false><<<clx::R * count, clx::THREADS, clx::Smem::bytes, (cudaStream_t)stream>>>(P, d_gates, count, vb.d_bkx, vb.d_twx,
+                                                                                                            vb.d_F, d_ext, d_acc_dbg);
   return (int)cudaGetLastError();
 }
 

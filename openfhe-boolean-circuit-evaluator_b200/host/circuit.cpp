@@ -176,7 +176,8 @@ static void free_device(bfhe_circuit *c) {
 // planning
 // ---------------------------------------------------------------------------------------------
 static int build_plan_cap(bfhe_circuit *c, uint32_t cap);
-static bool cluster_forms_available(const bfhe_ctx *x) { return x && x->v2.d_tw2 && x->p.method == BFHE_GINX; }
+static bool cluster_forms_available(const bfhe_ctx *x) { return x && x->v2.d_tw2 && x->p.method == BFHE_GINX; } // 2-CTA form (GINX)
+static bool clx_form_available(const bfhe_ctx *x) { return x && x->v2.d_twx; }                                   // 4-CTA form (GINX and AP)
 
 struct FormCaps { int sms = 0, cl2 = 0, cl4 = 0; };
 // cost (ms) of one wave of n bootstraps on ONE GPU: 4-CTA cluster form up to `cl4` gates, 2-CTA cluster form up to `cl2`, else the
@@ -206,9 +207,8 @@ static FormCaps form_caps(const bfhe_circuit *c) {
   // device's cudaOccupancyMaxActiveClusters (which differs between GPUs of one box: 74 and 63 two-CTA clusters were both seen on
   // 148-SM B200s): 5/12 of the SMs for one gate on two SMs, 2/9 for one gate on four.  A wave that a particular GPU cannot keep
   // co-resident in the planned form simply runs in the next form there (launch_blind_rotate checks the real limit).
-  const bool clusters = cluster_forms_available(c->ctx);
-  f.cl2 = clusters ? f.sms * 5 / 12 : 0;
-  f.cl4 = clusters ? f.sms * 2 / 9 : 0;
+  f.cl2 = cluster_forms_available(c->ctx) ? f.sms * 5 / 12 : 0;
+  f.cl4 = clx_form_available(c->ctx) ? f.sms * 2 / 9 : 0;
   return f;
 }
 static double plan_cost_ms(const bfhe_circuit *c, const FormCaps &f) {
@@ -607,7 +607,7 @@ static int probe_costs(bfhe_circuit *c) {
     const double dflt[4] = {FormCosts().cl4, FormCosts().cl2, FormCosts().lat, FormCosts().thr};
     for (int k = 0; k < 4; k++) {
       x->form_cost_ms[k] = dflt[k];
-      if (count[k] <= 0 || (k < 2 && !cluster_forms_available(x))) continue;
+      if (count[k] <= 0 || (k == 0 && !clx_form_available(x)) || (k == 1 && !cluster_forms_available(x))) continue;
       float best = 0;
       for (int rep = 0; rep < 3; rep++) { // first repetition warms the key into L2
         BFHE_CUDA(cudaEventRecord(e0, x->stream));

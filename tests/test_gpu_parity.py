@@ -53,8 +53,8 @@ def _random_gates(bfhe, rng, n_in, count, ops):
 @pytest.mark.parametrize("gpc", [4, 8, 32, 128])  # 32 = one gate on a 2-CTA cluster, 128 = one gate on a slot-sliced 4-CTA cluster (STD128_OPT GINX only)
 def test_blind_rotate_accumulator(bfhe, orc, ps_name, m_name, gpc):
     """a9-a12: accumulator after the whole blind rotation, coefficient form, vs the oracle's evaluation-form loop."""
-    if gpc >= 16 and (ps_name, m_name) != ("STD128_OPT", "GINX"):
-        pytest.skip("the cluster forms cover the STD128_OPT GINX shape only")
+    if gpc >= 16 and (ps_name, m_name) != ("STD128_OPT", "GINX") and (gpc, ps_name, m_name) != (128, "STD128_OPT", "AP"):
+        pytest.skip("the cluster forms cover the STD128_OPT shape only (2-CTA form: GINX only)")
     ctx, o = _setup(bfhe, orc, ps_name, m_name)
     rng = np.random.default_rng(3)
     bits = rng.integers(0, 2, size=6)
@@ -80,8 +80,8 @@ def test_blind_rotate_accumulator(bfhe, orc, ps_name, m_name, gpc):
 def test_bingate_bit_exact(bfhe, orc, ps_name, m_name, gpc):
     """a7: output LWE ciphertexts of a wavefront are bit-identical to the oracle for every gate type (the 12-op list: all eight
     BINGATE values, Bootstrap, and fused EvalNOT operands), on every kernel form, STD128_OPT AP included (a11)."""
-    if gpc >= 16 and (ps_name, m_name) != ("STD128_OPT", "GINX"):
-        pytest.skip("the cluster forms cover the STD128_OPT GINX shape only")
+    if gpc >= 16 and (ps_name, m_name) != ("STD128_OPT", "GINX") and (gpc, ps_name, m_name) != (128, "STD128_OPT", "AP"):
+        pytest.skip("the cluster forms cover the STD128_OPT shape only (2-CTA form: GINX only)")
     if (ps_name, m_name) == ("STD128_OPT", "AP") and gpc == 2:
         pytest.skip("AP STD128_OPT: forms 1, 4 and 8 cover the code paths; keeps the 2 GB-key run short")
     ctx, o = _setup(bfhe, orc, ps_name, m_name)
