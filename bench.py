@@ -483,9 +483,19 @@ def ap_line(B, device):
     dec = ctx.decrypt(slab.download(n_in, count))
     ok = bool(np.array_equal(dec, 1 - (bits[g["in0"]] & bits[g["in1"]])))
     rate = reps * count / dt
+    # one narrow wave (what a deep circuit's level costs with AP): the cost model's choice for 33 gates = the 4-CTA cluster form
+    ctx.eval_bingate_batch(slab, g[:33])
+    ctx.sync()
+    ctx.profile_enable(True)
+    ctx.eval_bingate_batch(slab, g[:33])
+    ctx.sync()
+    wave_br, _ = ctx.profile_read(0)
+    wave_ks, _ = ctx.profile_read(1)
+    ctx.profile_enable(False)
     slab.free()
     ctx.close()
     return {"metric": "bootstrapped gates/sec (STD128_OPT AP)", "value": rate, "gates_per_step": count, "decrypt_ok": ok,
+            "wave_33_gates_ms": {"blind_rotate": wave_br, "key_switch": wave_ks},
             "roofline": {"bound": "int", "achieved": rate * 3 * W_MODMUL_AP / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
                          "frac": rate * 3 * W_MODMUL_AP / imad_peak, "work_per_unit": "3 x 67.7M modular multiplications per gate (SURVEY 8(a) a11)"}}
 
