@@ -98,12 +98,6 @@ __device__ __forceinline__ u32 dsmem_addr(const void *local, u32 rank) { // shar
   return a;
 }
 // remote store whose arrival is counted on the destination CTA's mbarrier (complete_tx): the receiver needs no cluster-scope fence
-__device__ __forceinline__ void st_async4(u32 dsmem, uint4 v, u32 dsmem_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dsmem), "r"(v.x), "r"(v.y),
-               "r"(v.z), "r"(v.w), "r"(dsmem_bar)
-               : "memory");
-}
-
 __device__ __forceinline__ void st_async2(u32 dsmem, uint2 v, u32 dsmem_bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(dsmem), "r"(v.x), "r"(v.y), "r"(dsmem_bar)
                : "memory");
@@ -124,27 +118,8 @@ template <int T> __device__ __forceinline__ void ct8_stage(u32 (&x)[8], const u3
     x[a] = x[a] + t[i];
   }
 }
-// Gentleman-Sande stage; B = bound of the inputs in units of Q.  Sums are pulled back below 2Q when they would pass 32Q at the next stage.
-template <int T, int B> struct Gs8 {
-  static constexpr bool RED = (2 * B > 16);
-  static constexpr int OUTB = RED ? 2 : 2 * B;
-  __device__ __forceinline__ static void run(u32 (&x)[8], const u32 (&w)[8], const u32 (&ws)[8], u32 Q) {
-    static_assert(B <= 16, "GS input bound too large");
-    u32 D[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int g = i / T, a = g * 2 * T + (i % T), b = a + T;
-      D[i] = x[a] - x[b] + B * Q;
-      const u32 S = x[a] + x[b];
-      x[a] = RED ? lazy_reduce(S, Q) : S;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int g = i / T, b = g * 2 * T + (i % T) + T, p = 4 / T + g;
-      x[b] = mul_shoup(D[i], w[p], ws[p], Q);
-    }
-  }
-};
+// Gentleman-Sande stage; B = bound of the inputs in units of Q.  Sums double per stage and are pulled back below 2Q when they would pass 32Q
+// at the next stage (compile-time bound tracking through OUTB).
 template <int B> struct GsShfl1 { // one inverse stage across lanes `mask` apart on ONE value per thread; the upper lane holds b
   static constexpr bool RED = (2 * B > 16);
   static constexpr int OUTB = RED ? 2 : 2 * B;
