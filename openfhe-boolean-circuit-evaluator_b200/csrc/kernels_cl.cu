@@ -44,7 +44,7 @@
 namespace bfhe {
 namespace clx {
 
-constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, NPAD = 512, R = 4, NB = N / R, THREADS = 288; // 8 main warps + the warp that fetches the key tiles
+constexpr int LOGN = 10, N = 1 << LOGN, DG = 4, LOGBG = 7, ROWS = 2 * DG, R = 4, NB = N / R, THREADS = 288; // 8 main warps + the warp that fetches the key tiles
 constexpr int KEYPOLYS = 2 * ROWS * 2; // GINX: two RGSW ciphertexts (X^a, X^-a) per step; AP: one (KEYPOLYS / 2 polynomials)
 constexpr int NSTEP_PAD = 1024;     // >= n (GINX) and >= n * dR (AP)
 constexpr u32 DIGIT_OFF = 64u + (64u << 7) + (64u << 14) + (64u << 21);
